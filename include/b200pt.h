@@ -1,0 +1,175 @@
+/* libb200pt — C ABI of the B200 (sm_100a) kernels behind the data-parallel pretraining step.
+ *
+ * The reference (tttyuntian/multimodal_llm_pretraining) is pure Python: the arithmetic of its hot path lives in
+ * transformers / torch / deepspeed. There is therefore no native FFI in the reference to mirror; each
+ * entry point below names the third-party op it replaces on the path that `src/benchmarking/utils.py:61-80`
+ * (manual_training_step / manual_optimization_step) drives.  "HF:" = transformers/ (v5.5.0 in this image).
+ *
+ * Conventions:
+ *   - every function returns 0 on success, <0 on error; b200_last_error() gives a thread-local message;
+ *   - no C++ exceptions cross the ABI; no torch types; plain device pointers + sizes;
+ *   - the caller owns every buffer including workspaces; kernels never allocate and never synchronise the device;
+ *   - everything is enqueued on the cudaStream_t that is passed in (as void*);
+ *   - activations/weights feeding tensor cores are bf16; statistics, biases, LayerNorm affine, gradients of
+ *     parameters and optimizer state are fp32.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_ABI_VERSION 3
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+int b200_abi_version(void);
+const char* b200_last_error(void);
+/* One-time per-process/device setup: resolves cuTensorMapEncodeTiled, raises dynamic-smem limits. Idempotent. */
+int b200_init(int device);
+
+/* ---------------------------------------------------------------- LayerNorm
+ * Replaces nn.LayerNorm fwd/bwd (HF:models/gpt_neox/modeling_gpt_neox.py:251-252,269,279,376).
+ * x,y,dy,dx bf16 [rows, cols]; gamma/beta fp32; mean/rstd fp32 [rows].
+ * gamma2/beta2/y2 (nullable): second affine on the SAME normalised x — GPT-NeoX's parallel-residual block applies
+ * input_layernorm and post_attention_layernorm to the same tensor (modeling_gpt_neox.py:269,279). */
+int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, const float* gamma2,
+                       const float* beta2, void* y2, float* mean, float* rstd, int rows, int cols, float eps,
+                       b200_stream_t stream);
+/* dx = LN'(dy[,dy2]) (+ dres); dgamma/dbeta (+ second affine) are ACCUMULATED (+=) in fp32.
+ * workspace: b200_layernorm_bwd_workspace_bytes(cols, n_affine) bytes of scratch. */
+size_t b200_layernorm_bwd_workspace_bytes(int cols, int n_affine);
+int b200_layernorm_bwd(const void* x, const float* mean, const float* rstd, const float* gamma, const void* dy,
+                       const float* gamma2, const void* dy2, const void* dres, void* dx, float* dgamma, float* dbeta,
+                       float* dgamma2, float* dbeta2, void* workspace, size_t workspace_bytes, int rows, int cols,
+                       b200_stream_t stream);
+
+/* ---------------------------------------------------------------- GELU (exact erf; HF:activations.py GELUActivation) */
+int b200_gelu_fwd(const void* x, void* y, size_t n, b200_stream_t stream);
+int b200_gelu_bwd(const void* x, const void* dy, void* dx, size_t n, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Rotary embedding
+ * In-place NeoX rotate-half on the first `rot` dims of q and k inside a packed qkv buffer
+ * [B*S, nh, 3, hd] (HF:modeling_gpt_neox.py:119-159,211-222). cos/sin fp32 [S, rot/2].
+ * inverse=1 applies the transpose rotation (backward). */
+int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int B, int S, int nh, int hd, int rot,
+                         int inverse, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Embedding
+ * out[t,:] = table[ids[t],:] (HF:modeling_gpt_neox.py:345). bwd: dtable[ids[t],:] += dout[t,:] in fp32. */
+int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int T, int h, int vocab,
+                       b200_stream_t stream);
+int b200_embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int T, int h, int vocab,
+                       b200_stream_t stream);
+/* out[t,:] = LN-less sum of up to three bf16 table rows (RoBERTa word + position + token-type,
+ * HF:models/roberta/modeling_roberta.py:56-144); ids1/ids2 may be NULL. */
+int b200_embedding3_fwd(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1,
+                        const int64_t* ids2, const void* table2, void* out, int T, int h, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Cross entropy over the vocabulary
+ * Replaces ForCausalLMLoss / fixed_cross_entropy (HF:loss/loss_utils.py:28-67): fp32 log-softmax + NLL, mean over
+ * labels != ignore_index. logits bf16 [T, ld] (V valid columns) are overwritten IN PLACE by
+ * dlogits = (softmax - onehot) / n_valid when write_grad != 0.  row_loss fp32 [T]; n_valid device int (output of
+ * b200_count_valid); loss_out device fp32 scalar. */
+int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int* n_valid, b200_stream_t stream);
+int b200_cross_entropy(void* logits, const int64_t* labels, float* row_loss, const int* n_valid, int T, int V,
+                       int64_t ld, int64_t ignore_index, int write_grad, b200_stream_t stream);
+int b200_mean_loss(const float* row_loss, const int* n_valid, int T, float* loss_out, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- GEMM on tcgen05 / TMEM / TMA
+ * C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )  — replaces nn.Linear fwd / dgrad / wgrad (cuBLAS in the reference
+ * stack; HF:modeling_gpt_neox.py:41-42,200-201,464).
+ *   a_mn = 0: A stored [M, K] row-major (lda = row pitch in elements);  a_mn = 1: A stored [K, M] row-major.
+ *   b_mn = 0: B stored [N, K] row-major;                                b_mn = 1: B stored [K, N] row-major.
+ *   fwd   y = x W^T      : a_mn 0, b_mn 0 (W [out,in])
+ *   dgrad dx = dy W      : a_mn 0, b_mn 1
+ *   wgrad dW = dy^T x    : a_mn 1, b_mn 1, c_fp32 = 1, accumulate = 1
+ * epilogue order: acc*alpha -> +bias[n] -> gelu -> +residual[m,n] -> (+C if accumulate) -> store (bf16 or fp32).
+ * aux_out (nullable, bf16 [M,N], ld = ldc): receives the value BEFORE gelu (pre-activation kept for backward).
+ * dgelu_in (nullable, bf16 [M,N], ld = ldr): value is multiplied by gelu'(dgelu_in[m,n]) (fused dGELU for dgrad). */
+typedef struct b200_gemm_args {
+    int M, N, K;
+    const void* A;
+    int64_t lda;
+    int a_mn;
+    const void* B;
+    int64_t ldb;
+    int b_mn;
+    void* C;
+    int64_t ldc;
+    int c_fp32;
+    int accumulate;
+    const float* bias;      /* fp32 [N] or NULL */
+    const void* residual;   /* bf16 [M, ldr] or NULL */
+    int64_t ldr;
+    int gelu;
+    const float* alpha_dev; /* device fp32 scalar or NULL (=1) */
+    void* aux_out;          /* bf16 or NULL */
+    const void* dgelu_in;   /* bf16 or NULL */
+} b200_gemm_args;
+int b200_gemm_bf16(const b200_gemm_args* args, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Flash attention on tcgen05
+ * Replaces F.scaled_dot_product_attention(is_causal=True) (HF:integrations/sdpa_attention.py:92-101) and RoBERTa's
+ * eager softmax attention (HF:models/roberta/modeling_roberta.py:162-187) with causal=0.
+ * q,k,v,o,do,dq,dk,dv: bf16; token t = b*S+s, head hh element d at  ptr[t*row_stride + hh*head_stride + d].
+ * lse, delta: fp32 [B, H, S].  D in {64, 128, 256}.  scale = head_dim^-0.5. */
+typedef struct b200_attn_args {
+    int B, S, H, D;
+    int causal;
+    float scale;
+    const void* q;
+    const void* k;
+    const void* v;
+    int64_t qkv_row_stride;   /* elements between tokens in q/k/v buffers */
+    int64_t qkv_head_stride;  /* elements between heads */
+    void* o;                  /* fwd out / bwd in */
+    int64_t o_row_stride;
+    int64_t o_head_stride;
+    float* lse;               /* fwd out / bwd in */
+    /* backward only */
+    const void* d_o;          /* same layout as o */
+    float* delta;             /* scratch [B,H,S] */
+    void* dq;
+    void* dk;
+    void* dv;                 /* same layout as q/k/v (dqkv_* strides) */
+    int64_t dqkv_row_stride;
+    int64_t dqkv_head_stride;
+} b200_attn_args;
+int b200_attention_fwd(const b200_attn_args* args, b200_stream_t stream);
+int b200_attention_bwd(const b200_attn_args* args, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Optimizer (fused multi-tensor Adam / AdamW)
+ * Replaces torch.optim.Adam foreach path and DeepSpeed FusedAdam (src/models/pythia.py:43-67, src/train.py:157-167).
+ * All parameters live in one flat fp32 buffer; `chunks` partition the part this rank updates into pieces that each
+ * belong to one param group. p/g are indexed by absolute element offset; m/v by (offset - state_base) so that a
+ * ZeRO-1 shard can keep only its slice of the moments.
+ *   adamw_mode = 0: L2 (torch.optim.Adam):  g += wd*p          adamw_mode = 1: decoupled (p *= 1 - lr*wd)
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+ * grad_scale_dev (nullable): device fp32 scalar multiplied into every gradient first (clip coefficient / unscale).
+ * p_bf16 (nullable): bf16 shadow of p written in the same pass. zero_grad != 0 clears g in the same pass. */
+typedef struct b200_adam_group {
+    float lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2;
+    int adamw_mode;
+} b200_adam_group;
+#define B200_ADAM_MAX_GROUPS 8
+int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
+                   const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks,
+                   const b200_adam_group* groups, int n_groups, const float* grad_scale_dev, int zero_grad,
+                   b200_stream_t stream);
+/* out[0] += sum(x[i]^2) (fp32 atomics over per-block partials). */
+int b200_sumsq(const float* x, size_t n, float* out, b200_stream_t stream);
+/* norm_out = sqrt(sumsq); coef_out = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_ semantics);
+ * max_norm <= 0 gives coef 1. */
+int b200_clip_coef(const float* sumsq, float max_norm, float* norm_out, float* coef_out, b200_stream_t stream);
+int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200_stream_t stream);
+int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PT_H */

@@ -1,0 +1,271 @@
+// HBM-bound elementwise / gather kernels: exact-erf GELU, in-place partial rotary on packed qkv, embedding gather and
+// scatter-add, dtype casts.  16-byte vector accesses, grid-stride loops sized to a multiple of the SM count.
+#include "api.h"
+#include "common.cuh"
+
+namespace b200 {
+
+static inline int ew_grid(size_t n_vec, int threads) {
+    size_t blocks = (n_vec + threads - 1) / threads;
+    const size_t cap = static_cast<size_t>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+// ----------------------------------------------------------------------------------------------- GELU
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t n_vec) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4 v = ld_nc_v4(x + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = bf2_to_f2(w[j]);
+            o[j] = f2_to_bf2(gelu_erf(f.x), gelu_erf(f.y));
+        }
+        st_v4(y + i, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, size_t n_vec) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4 v = ld_nc_v4(x + i);
+        const uint4 g = ld_nc_v4(dy + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = bf2_to_f2(w[j]);
+            const float2 d = bf2_to_f2(gw[j]);
+            o[j] = f2_to_bf2(d.x * gelu_erf_grad(f.x), d.y * gelu_erf_grad(f.y));
+        }
+        st_v4(dx + i, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- RoPE
+// One thread handles one (token, head, which in {q,k}, pair-of-8) : 8 low dims [i0,i0+8) and their partners at +rot/2.
+// When rot/2 is not a multiple of 8 (e.g. rot=20 for pythia-2.8b) falls back to a scalar pair-per-thread kernel.
+__global__ void __launch_bounds__(256)
+rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                int T, int S, int nh, int hd, int half, int inverse) {
+    const int vec_per = half / 8;  // vectors per (token, head, q|k)
+    const size_t total = static_cast<size_t>(T) * nh * 2 * vec_per;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int vi = static_cast<int>(idx % vec_per);
+        size_t r = idx / vec_per;
+        const int which = static_cast<int>(r % 2);
+        r /= 2;
+        const int head = static_cast<int>(r % nh);
+        const int t = static_cast<int>(r / nh);
+        const int pos = t % S;
+        __nv_bfloat16* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + vi * 8;
+        const uint4 lo = *reinterpret_cast<const uint4*>(base);
+        const uint4 hi = *reinterpret_cast<const uint4*>(base + half);
+        const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w};
+        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+        const float* c = cos_tab + static_cast<size_t>(pos) * half + vi * 8;
+        const float* s = sin_tab + static_cast<size_t>(pos) * half + vi * 8;
+        uint32_t ol[4], oh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = bf2_to_f2(lw[j]);
+            const float2 b = bf2_to_f2(hw[j]);
+            const float c0 = c[2 * j], c1 = c[2 * j + 1];
+            float s0 = s[2 * j], s1 = s[2 * j + 1];
+            if (inverse) s0 = -s0, s1 = -s1;
+            // out_lo = lo*cos - hi*sin ; out_hi = hi*cos + lo*sin   (HF apply_rotary_pos_emb / rotate_half)
+            ol[j] = f2_to_bf2(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1);
+            oh[j] = f2_to_bf2(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1);
+        }
+        *reinterpret_cast<uint4*>(base) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        *reinterpret_cast<uint4*>(base + half) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    }
+}
+__global__ void __launch_bounds__(256)
+rope_scalar_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                   int T, int S, int nh, int hd, int half, int inverse) {
+    const size_t total = static_cast<size_t>(T) * nh * 2 * half;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(idx % half);
+        size_t r = idx / half;
+        const int which = static_cast<int>(r % 2);
+        r /= 2;
+        const int head = static_cast<int>(r % nh);
+        const int t = static_cast<int>(r / nh);
+        const int pos = t % S;
+        __nv_bfloat16* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + i;
+        const float a = bf_to_f(base[0]), b = bf_to_f(base[half]);
+        const float c = cos_tab[static_cast<size_t>(pos) * half + i];
+        float s = sin_tab[static_cast<size_t>(pos) * half + i];
+        if (inverse) s = -s;
+        base[0] = __float2bfloat16_rn(a * c - b * s);
+        base[half] = __float2bfloat16_rn(b * c + a * s);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- Embedding
+// one warp per token row; 16-byte vectors
+__global__ void __launch_bounds__(256)
+embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __restrict__ t0,
+                     const int64_t* __restrict__ ids1, const __nv_bfloat16* __restrict__ t1,
+                     const int64_t* __restrict__ ids2, const __nv_bfloat16* __restrict__ t2,
+                     __nv_bfloat16* __restrict__ out, int T, int h) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
+        const __nv_bfloat16* r0 = t0 + static_cast<size_t>(ids0[t]) * h;
+        const __nv_bfloat16* r1 = ids1 ? t1 + static_cast<size_t>(ids1[t]) * h : nullptr;
+        const __nv_bfloat16* r2 = ids2 ? t2 + static_cast<size_t>(ids2[t]) * h : nullptr;
+        __nv_bfloat16* o = out + static_cast<size_t>(t) * h;
+        for (int c = lane * 8; c < h; c += 256) {
+            uint4 v = *reinterpret_cast<const uint4*>(r0 + c);
+            if (r1 || r2) {
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a = bf2_to_f2(w[j]);
+                    f[2 * j] = a.x, f[2 * j + 1] = a.y;
+                }
+                if (r1) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(r1 + c);
+                    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = bf2_to_f2(uw[j]);
+                        f[2 * j] += a.x, f[2 * j + 1] += a.y;
+                    }
+                }
+                if (r2) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(r2 + c);
+                    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 a = bf2_to_f2(uw[j]);
+                        f[2 * j] += a.x, f[2 * j + 1] += a.y;
+                    }
+                }
+                v = make_uint4(f2_to_bf2(f[0], f[1]), f2_to_bf2(f[2], f[3]), f2_to_bf2(f[4], f[5]), f2_to_bf2(f[6], f[7]));
+            }
+            st_v4(o + c, v);
+        }
+    }
+}
+// scatter-add into fp32 table gradient. Random ids over a 50k vocab rarely collide, so plain fp32 REDs are cheap.
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dout, float* __restrict__ dtable,
+                     int T, int h) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
+        float* drow = dtable + static_cast<size_t>(ids[t]) * h;
+        const __nv_bfloat16* g = dout + static_cast<size_t>(t) * h;
+        for (int c = lane * 8; c < h; c += 256) {
+            const uint4 v = ld_nc_v4(g + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = bf2_to_f2(w[j]);
+                atomicAdd(drow + c + 2 * j, a.x);
+                atomicAdd(drow + c + 2 * j + 1, a.y);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- casts
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n_vec4) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = src[i];
+        dst[i] = make_uint2(f2_to_bf2(v.x, v.y), f2_to_bf2(v.z, v.w));
+    }
+}
+__global__ void cast_f32_bf16_tail(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t start, size_t n) {
+    const size_t i = start + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void __launch_bounds__(256)
+scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scale_dev, float scale_host) {
+    const float s = (scale_dev ? *scale_dev : 1.0f) * scale_host;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        x[i] *= s;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gelu_fwd(const void* x, void* y, size_t n, b200_stream_t stream) {
+    B200_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(y), "gelu_fwd: n must be a multiple of 8 and pointers 16B aligned");
+    const size_t nv = n / 8;
+    gelu_fwd_kernel<<<ew_grid(nv, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), nv);
+    return check_launch("gelu_fwd");
+}
+extern "C" int b200_gelu_bwd(const void* x, const void* dy, void* dx, size_t n, b200_stream_t stream) {
+    B200_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx), "gelu_bwd: n must be a multiple of 8 and pointers 16B aligned");
+    const size_t nv = n / 8;
+    gelu_bwd_kernel<<<ew_grid(nv, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(dy), static_cast<uint4*>(dx), nv);
+    return check_launch("gelu_bwd");
+}
+
+extern "C" int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float* sin_tab, int B, int S, int nh, int hd,
+                                    int rot, int inverse, b200_stream_t stream) {
+    B200_REQUIRE(rot > 0 && rot % 2 == 0 && rot <= hd, "rope: rot (%d) must be even and <= head_dim (%d)", rot, hd);
+    const int half = rot / 2;
+    const int T = B * S;
+    auto p = static_cast<__nv_bfloat16*>(qkv);
+    if (half % 8 == 0 && hd % 8 == 0 && aligned16(qkv)) {
+        const size_t total = static_cast<size_t>(T) * nh * 2 * (half / 8);
+        rope_vec_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
+    } else {
+        const size_t total = static_cast<size_t>(T) * nh * 2 * half;
+        rope_scalar_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
+    }
+    return check_launch("rope_qk_inplace");
+}
+
+extern "C" int b200_embedding3_fwd(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1,
+                                   const int64_t* ids2, const void* table2, void* out, int T, int h,
+                                   b200_stream_t stream) {
+    B200_REQUIRE(h % 8 == 0 && aligned16(table0) && aligned16(out), "embedding_fwd: h must be a multiple of 8, pointers 16B aligned");
+    const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
+    embedding_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+        ids0, static_cast<const __nv_bfloat16*>(table0), ids1, static_cast<const __nv_bfloat16*>(table1), ids2,
+        static_cast<const __nv_bfloat16*>(table2), static_cast<__nv_bfloat16*>(out), T, h);
+    return check_launch("embedding_fwd");
+}
+extern "C" int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int T, int h, int vocab,
+                                  b200_stream_t stream) {
+    (void)vocab;
+    return b200_embedding3_fwd(ids, table, nullptr, nullptr, nullptr, nullptr, out, T, h, stream);
+}
+extern "C" int b200_embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int T, int h, int vocab,
+                                  b200_stream_t stream) {
+    (void)vocab;
+    B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
+    const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
+    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h);
+    return check_launch("embedding_bwd");
+}
+
+extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200_stream_t stream) {
+    B200_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0, "cast: src must be 16B and dst 8B aligned");
+    const size_t n4 = n / 4;
+    if (n4) cast_f32_bf16_kernel<<<ew_grid(n4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n4);
+    if (n % 4) cast_f32_bf16_tail<<<1, 32, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n4 * 4, n);
+    return check_launch("cast_f32_to_bf16");
+}
+extern "C" int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream) {
+    scale_f32_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, scale_dev, scale_host);
+    return check_launch("scale_f32");
+}

@@ -1,0 +1,371 @@
+// Fused LayerNorm forward/backward (HBM-bound).  Replaces nn.LayerNorm as used by GPT-NeoX
+// (HF:models/gpt_neox/modeling_gpt_neox.py:251-252,269,279,376) and RoBERTa (HF:models/roberta/modeling_roberta.py).
+//
+// Layout: x bf16 [rows, cols] row-major; a row is owned by G consecutive warps (G=1 for cols<=2048), each lane keeps
+// NV 16-byte vectors (8 bf16) of the row in registers, so x is read from HBM exactly once.  Statistics in fp32,
+// two-pass (mean, then centred sum of squares) on the register copy.  Optional second affine (gamma2/beta2 -> y2) for
+// GPT-NeoX's parallel block, which normalises the same x twice: one read, two writes.
+//
+// Algorithmic bytes: fwd 2*cols (read) + 2*cols*NA (write) per row; bwd 2*cols*(1 + NA [+1 dres]) read + 2*cols write.
+#include "api.h"
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float group_sum(float v, int G, float* red) {
+    v = warp_sum(v);
+    if (G == 1) return v;
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 0) red[warp] = v;
+    __syncthreads();
+    const int base = (warp / G) * G;
+    float t = 0.f;
+    for (int j = 0; j < G; ++j) t += red[base + j];
+    __syncthreads();
+    return t;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
+              __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
+              __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+              int cols, float eps, int G) {
+    __shared__ float red[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows_per_block = 4 / G;
+    const int sub = warp % G;
+    const int row = blockIdx.x * rows_per_block + warp / G;
+    const bool row_ok = row < rows;
+    const size_t roff = static_cast<size_t>(row) * cols;
+
+    uint4 xv[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = ((i * G + sub) * 32 + lane) * 8;
+        if (row_ok && col < cols) {
+            xv[i] = ld_nc_v4(x + roff + col);
+            const float2 a = bf2_to_f2(xv[i].x), b = bf2_to_f2(xv[i].y), c = bf2_to_f2(xv[i].z), d = bf2_to_f2(xv[i].w);
+            sum += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+        } else {
+            xv[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    const float mean = group_sum(sum, G, red) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = ((i * G + sub) * 32 + lane) * 8;
+        if (col < cols) {
+            const uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf2_to_f2(w[j]);
+                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+            }
+        }
+    }
+    const float var = group_sum(sq, G, red) / cols;
+    const float rstd = rsqrtf(var + eps);
+    if (row_ok && sub == 0 && lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+    if (!row_ok) return;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = ((i * G + sub) * 32 + lane) * 8;
+        if (col < cols) {
+            const uint32_t w[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+            float xh[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf2_to_f2(w[j]);
+                xh[2 * j] = (f.x - mean) * rstd;
+                xh[2 * j + 1] = (f.y - mean) * rstd;
+            }
+            {
+                const float4 ga = __ldg(reinterpret_cast<const float4*>(g1 + col));
+                const float4 gb = __ldg(reinterpret_cast<const float4*>(g1 + col + 4));
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(b1 + col));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col + 4));
+                uint4 o;
+                o.x = f2_to_bf2(xh[0] * ga.x + ba.x, xh[1] * ga.y + ba.y);
+                o.y = f2_to_bf2(xh[2] * ga.z + ba.z, xh[3] * ga.w + ba.w);
+                o.z = f2_to_bf2(xh[4] * gb.x + bb.x, xh[5] * gb.y + bb.y);
+                o.w = f2_to_bf2(xh[6] * gb.z + bb.z, xh[7] * gb.w + bb.w);
+                st_v4(y1 + roff + col, o);
+            }
+            if (g2 != nullptr) {
+                const float4 ga = __ldg(reinterpret_cast<const float4*>(g2 + col));
+                const float4 gb = __ldg(reinterpret_cast<const float4*>(g2 + col + 4));
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(b2 + col));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + col + 4));
+                uint4 o;
+                o.x = f2_to_bf2(xh[0] * ga.x + ba.x, xh[1] * ga.y + ba.y);
+                o.y = f2_to_bf2(xh[2] * ga.z + ba.z, xh[3] * ga.w + ba.w);
+                o.z = f2_to_bf2(xh[4] * gb.x + bb.x, xh[5] * gb.y + bb.y);
+                o.w = f2_to_bf2(xh[6] * gb.z + bb.z, xh[7] * gb.w + bb.w);
+                st_v4(y2 + roff + col, o);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward.  Persistent: one 256-thread block per SM loops over rows; each lane accumulates dgamma/dbeta for the
+// columns it owns in registers, block partials go to the workspace, ln_bwd_finalize sums them deterministically and
+// accumulates (+=) into the fp32 parameter-gradient buffers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NV, int NA>
+__global__ void __launch_bounds__(256, 1)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const float* __restrict__ g1, const __nv_bfloat16* __restrict__ dy1, const float* __restrict__ g2,
+              const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ dres,
+              __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int rows, int cols, int G) {
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows_per_block = 8 / G;
+    const int sub = warp % G;
+    const int slot = warp / G;
+    const float inv_cols = 1.0f / cols;
+
+    float acc_g[NA][NV * 8], acc_b[NA][NV * 8];
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int i = 0; i < NV * 8; ++i) acc_g[a][i] = 0.f, acc_b[a][i] = 0.f;
+
+    const int n_iter = (rows + rows_per_block * gridDim.x - 1) / (rows_per_block * gridDim.x);
+    for (int it = 0; it < n_iter; ++it) {
+        const int row = (it * gridDim.x + blockIdx.x) * rows_per_block + slot;
+        const bool row_ok = row < rows;
+        const size_t roff = static_cast<size_t>(row) * cols;
+        const float mean = row_ok ? mean_in[row] : 0.f;
+        const float rstd = row_ok ? rstd_in[row] : 0.f;
+
+        float xh[NV * 8], dxh[NV * 8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = ((i * G + sub) * 32 + lane) * 8;
+            const bool ok = row_ok && col < cols;
+            uint4 xv = make_uint4(0, 0, 0, 0), d1 = xv, d2 = xv;
+            if (ok) {
+                xv = ld_nc_v4(x + roff + col);
+                d1 = ld_nc_v4(dy1 + roff + col);
+                if (NA == 2) d2 = ld_nc_v4(dy2 + roff + col);
+            }
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            const uint32_t w1[4] = {d1.x, d1.y, d1.z, d1.w};
+            const uint32_t w2[4] = {d2.x, d2.y, d2.z, d2.w};
+            float ga[8], gb[8];
+            if (ok) {
+                *reinterpret_cast<float4*>(&ga[0]) = __ldg(reinterpret_cast<const float4*>(g1 + col));
+                *reinterpret_cast<float4*>(&ga[4]) = __ldg(reinterpret_cast<const float4*>(g1 + col + 4));
+                if (NA == 2) {
+                    *reinterpret_cast<float4*>(&gb[0]) = __ldg(reinterpret_cast<const float4*>(g2 + col));
+                    *reinterpret_cast<float4*>(&gb[4]) = __ldg(reinterpret_cast<const float4*>(g2 + col + 4));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ga[j] = 0.f, gb[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 xf = bf2_to_f2(xw[j]);
+                const float2 a = bf2_to_f2(w1[j]);
+                const float h0 = ok ? (xf.x - mean) * rstd : 0.f;
+                const float h1 = ok ? (xf.y - mean) * rstd : 0.f;
+                float t0 = a.x * ga[2 * j], t1 = a.y * ga[2 * j + 1];
+                acc_g[0][i * 8 + 2 * j] += a.x * h0;
+                acc_g[0][i * 8 + 2 * j + 1] += a.y * h1;
+                acc_b[0][i * 8 + 2 * j] += a.x;
+                acc_b[0][i * 8 + 2 * j + 1] += a.y;
+                if (NA == 2) {
+                    const float2 b = bf2_to_f2(w2[j]);
+                    t0 += b.x * gb[2 * j];
+                    t1 += b.y * gb[2 * j + 1];
+                    acc_g[NA - 1][i * 8 + 2 * j] += b.x * h0;
+                    acc_g[NA - 1][i * 8 + 2 * j + 1] += b.y * h1;
+                    acc_b[NA - 1][i * 8 + 2 * j] += b.x;
+                    acc_b[NA - 1][i * 8 + 2 * j + 1] += b.y;
+                }
+                xh[i * 8 + 2 * j] = h0;
+                xh[i * 8 + 2 * j + 1] = h1;
+                dxh[i * 8 + 2 * j] = t0;
+                dxh[i * 8 + 2 * j + 1] = t1;
+                s1 += t0 + t1;
+                s2 += t0 * h0 + t1 * h1;
+            }
+        }
+        s1 = group_sum(s1, G, red) * inv_cols;
+        s2 = group_sum(s2, G, red) * inv_cols;
+        if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = ((i * G + sub) * 32 + lane) * 8;
+                if (col < cols) {
+                    float r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = rstd * (dxh[i * 8 + j] - s1 - xh[i * 8 + j] * s2);
+                    if (dres != nullptr) {
+                        const uint4 dv = ld_nc_v4(dres + roff + col);
+                        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = bf2_to_f2(dw[j]);
+                            r[2 * j] += f.x;
+                            r[2 * j + 1] += f.y;
+                        }
+                    }
+                    uint4 o;
+                    o.x = f2_to_bf2(r[0], r[1]);
+                    o.y = f2_to_bf2(r[2], r[3]);
+                    o.z = f2_to_bf2(r[4], r[5]);
+                    o.w = f2_to_bf2(r[6], r[7]);
+                    st_v4(dx + roff + col, o);
+                }
+            }
+        }
+    }
+    // partial layout: [gridDim.x * rows_per_block][NA][2][cols]
+    float* prow = partial + (static_cast<size_t>(blockIdx.x) * rows_per_block + slot) * (NA * 2) * cols;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = ((i * G + sub) * 32 + lane) * 8;
+            if (col < cols) {
+                float* pg = prow + (a * 2 + 0) * cols + col;
+                float* pb = prow + (a * 2 + 1) * cols + col;
+                *reinterpret_cast<float4*>(pg) = make_float4(acc_g[a][i * 8], acc_g[a][i * 8 + 1], acc_g[a][i * 8 + 2], acc_g[a][i * 8 + 3]);
+                *reinterpret_cast<float4*>(pg + 4) = make_float4(acc_g[a][i * 8 + 4], acc_g[a][i * 8 + 5], acc_g[a][i * 8 + 6], acc_g[a][i * 8 + 7]);
+                *reinterpret_cast<float4*>(pb) = make_float4(acc_b[a][i * 8], acc_b[a][i * 8 + 1], acc_b[a][i * 8 + 2], acc_b[a][i * 8 + 3]);
+                *reinterpret_cast<float4*>(pb + 4) = make_float4(acc_b[a][i * 8 + 4], acc_b[a][i * 8 + 5], acc_b[a][i * 8 + 6], acc_b[a][i * 8 + 7]);
+            }
+        }
+    }
+}
+
+// out[a][k][c] += sum_p partial[p][a][k][c];  block = 32 columns x 8 row-lanes.
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize(const float* __restrict__ partial, int n_partial, int n_arrays, int cols, float* o0, float* o1,
+                float* o2, float* o3) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int arr = blockIdx.y;
+    const int col = blockIdx.x * 32 + cx;
+    float s = 0.f;
+    if (col < cols) {
+        const float* base = partial + static_cast<size_t>(arr) * cols + col;
+        const size_t stride = static_cast<size_t>(n_arrays) * cols;
+        for (int p = ry; p < n_partial; p += 8) s += base[p * stride];
+    }
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && col < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][cx];
+        float* out = arr == 0 ? o0 : arr == 1 ? o1 : arr == 2 ? o2 : o3;
+        out[col] += t;
+    }
+}
+
+static int pick_group(int cols, int budget_cols, int max_g) {
+    int g = 1;
+    while (g < max_g && cols > budget_cols * g) g *= 2;
+    return g;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, const float* gamma2,
+                                  const float* beta2, void* y2, float* mean, float* rstd, int rows, int cols, float eps,
+                                  b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0, "layernorm_fwd: cols (%d) must be a positive multiple of 8", cols);
+    B200_REQUIRE(cols <= 8192, "layernorm_fwd: cols %d > 8192 unsupported", cols);
+    B200_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm_fwd: pointers must be 16-byte aligned");
+    B200_REQUIRE((gamma2 == nullptr) == (y2 == nullptr) && (gamma2 == nullptr) == (beta2 == nullptr), "layernorm_fwd: gamma2/beta2/y2 must be all set or all NULL");
+    const int G = pick_group(cols, 2048, 4);
+    const int nv = (cols + 256 * G - 1) / (256 * G);
+    const int rows_per_block = 4 / G;
+    dim3 grid((rows + rows_per_block - 1) / rows_per_block);
+    auto xs = static_cast<const __nv_bfloat16*>(x);
+    auto y1s = static_cast<__nv_bfloat16*>(y);
+    auto y2s = static_cast<__nv_bfloat16*>(y2);
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(NVV) ln_fwd_kernel<NVV><<<grid, 128, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G)
+    switch (nv) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        case 4: LAUNCH(4); break;
+        case 5: LAUNCH(5); break;
+        case 6: LAUNCH(6); break;
+        case 7: case 8: LAUNCH(8); break;
+        default: return fail(-1, "layernorm_fwd: unsupported cols %d", cols);
+    }
+#undef LAUNCH
+    return check_launch("layernorm_fwd");
+}
+
+extern "C" size_t b200_layernorm_bwd_workspace_bytes(int cols, int n_affine) {
+    return static_cast<size_t>(num_sms()) * 8 * n_affine * 2 * cols * sizeof(float);
+}
+
+extern "C" int b200_layernorm_bwd(const void* x, const float* mean, const float* rstd, const float* gamma,
+                                  const void* dy, const float* gamma2, const void* dy2, const void* dres, void* dx,
+                                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, void* workspace,
+                                  size_t workspace_bytes, int rows, int cols, b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 8192, "layernorm_bwd: bad cols %d", cols);
+    const int NA = gamma2 ? 2 : 1;
+    B200_REQUIRE((gamma2 == nullptr) == (dy2 == nullptr), "layernorm_bwd: gamma2/dy2 must both be set or NULL");
+    B200_REQUIRE(workspace_bytes >= b200_layernorm_bwd_workspace_bytes(cols, NA), "layernorm_bwd: workspace too small");
+    B200_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(workspace) && aligned16(gamma), "layernorm_bwd: pointers must be 16-byte aligned");
+    // registers: NV*NA <= 4 vectors per lane (dgamma/dbeta accumulators + xhat/dxhat copies stay under 255 regs)
+    const int G = pick_group(cols * NA, 1024, 8);
+    const int nv = (cols + 256 * G - 1) / (256 * G);
+    const int rows_per_block = 8 / G;
+    int grid = num_sms();
+    const int max_blocks = (rows + rows_per_block - 1) / rows_per_block;
+    if (grid > max_blocks) grid = max_blocks;
+    auto xs = static_cast<const __nv_bfloat16*>(x);
+    auto d1 = static_cast<const __nv_bfloat16*>(dy);
+    auto d2 = static_cast<const __nv_bfloat16*>(dy2);
+    auto dr = static_cast<const __nv_bfloat16*>(dres);
+    auto dxs = static_cast<__nv_bfloat16*>(dx);
+    float* part = static_cast<float*>(workspace);
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(NVV, NAA) ln_bwd_kernel<NVV, NAA><<<grid, 256, 0, st>>>(xs, mean, rstd, gamma, d1, gamma2, d2, dr, dxs, part, rows, cols, G)
+    if (NA == 1) {
+        switch (nv) {
+            case 1: LAUNCH(1, 1); break;
+            case 2: LAUNCH(2, 1); break;
+            case 3: LAUNCH(3, 1); break;
+            case 4: LAUNCH(4, 1); break;
+            case 5: LAUNCH(5, 1); break;
+            case 6: LAUNCH(6, 1); break;
+            case 7: case 8: LAUNCH(8, 1); break;
+            default: return fail(-1, "layernorm_bwd: unsupported cols %d", cols);
+        }
+    } else {
+        switch (nv) {
+            case 1: LAUNCH(1, 2); break;
+            case 2: LAUNCH(2, 2); break;
+            case 3: LAUNCH(3, 2); break;
+            case 4: LAUNCH(4, 2); break;
+            default: return fail(-1, "layernorm_bwd: unsupported cols %d (dual)", cols);
+        }
+    }
+#undef LAUNCH
+    int rc = check_launch("layernorm_bwd");
+    if (rc) return rc;
+    dim3 fgrid((cols + 31) / 32, NA * 2);
+    ln_bwd_finalize<<<fgrid, 256, 0, st>>>(part, grid * rows_per_block, NA * 2, cols, dgamma, dbeta, dgamma2, dbeta2);
+    return check_launch("layernorm_bwd_finalize");
+}

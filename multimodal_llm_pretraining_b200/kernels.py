@@ -1,0 +1,268 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point, no autograd, no fallbacks).
+
+Every function enqueues on torch's current CUDA stream and returns immediately. Shapes/dtypes are validated here so the
+C side only sees well-formed raw pointers.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import AdamGroup, AttnArgs, GemmArgs, check, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _L(t: torch.Tensor):
+    return _lib.lib_for(t.device)
+
+
+def _req(cond: bool, msg: str) -> None:
+    if not cond:
+        raise ValueError(msg)
+
+
+# ----------------------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, eps, gamma2=None, beta2=None):
+    """x bf16 [rows, cols] -> (y, y2|None, mean, rstd)."""
+    _req(x.dtype == BF16 and x.is_contiguous() and x.dim() == 2, "layernorm_fwd: x must be contiguous bf16 [rows, cols]")
+    _req(gamma.dtype == F32 and beta.dtype == F32, "layernorm_fwd: gamma/beta must be fp32")
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    y2 = torch.empty_like(x) if gamma2 is not None else None
+    mean = torch.empty(rows, dtype=F32, device=x.device)
+    rstd = torch.empty(rows, dtype=F32, device=x.device)
+    check(_L(x).b200_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(gamma2), ptr(beta2), ptr(y2), ptr(mean),
+                                   ptr(rstd), rows, cols, float(eps), stream_ptr()), "b200_layernorm_fwd")
+    return y, y2, mean, rstd
+
+
+_ws_cache: dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def layernorm_bwd(x, mean, rstd, gamma, dy, dgamma, dbeta, gamma2=None, dy2=None, dgamma2=None, dbeta2=None, dres=None):
+    """Returns dx (bf16). dgamma/dbeta (fp32) are accumulated in place."""
+    rows, cols = x.shape
+    _req(dy.dtype == BF16 and dy.is_contiguous() and dy.shape == x.shape, "layernorm_bwd: dy must match x")
+    _req(dgamma.dtype == F32 and dbeta.dtype == F32, "layernorm_bwd: dgamma/dbeta must be fp32")
+    lib = _L(x)
+    na = 2 if gamma2 is not None else 1
+    nbytes = lib.b200_layernorm_bwd_workspace_bytes(cols, na)
+    ws = _workspace(x.device, nbytes)
+    dx = torch.empty_like(x)
+    check(lib.b200_layernorm_bwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dy), ptr(gamma2), ptr(dy2), ptr(dres),
+                                 ptr(dx), ptr(dgamma), ptr(dbeta), ptr(dgamma2), ptr(dbeta2), ptr(ws), ws.numel(), rows,
+                                 cols, stream_ptr()), "b200_layernorm_bwd")
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------------- GELU / RoPE
+def gelu_fwd(x):
+    _req(x.dtype == BF16 and x.is_contiguous(), "gelu_fwd: contiguous bf16 expected")
+    y = torch.empty_like(x)
+    check(_L(x).b200_gelu_fwd(ptr(x), ptr(y), x.numel(), stream_ptr()), "b200_gelu_fwd")
+    return y
+
+
+def gelu_bwd(x, dy):
+    _req(x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous(), "gelu_bwd: contiguous bf16 expected")
+    dx = torch.empty_like(x)
+    check(_L(x).b200_gelu_bwd(ptr(x), ptr(dy), ptr(dx), x.numel(), stream_ptr()), "b200_gelu_bwd")
+    return dx
+
+
+def rope_qk_inplace(qkv, cos, sin, B, S, nh, hd, rot, inverse=False):
+    """qkv bf16 [B*S, nh*3*hd] packed per head as [q|k|v]; cos/sin fp32 [S, rot/2]."""
+    _req(qkv.dtype == BF16 and qkv.is_contiguous() and qkv.numel() == B * S * nh * 3 * hd, "rope: bad qkv")
+    _req(cos.dtype == F32 and sin.dtype == F32 and cos.is_contiguous() and sin.is_contiguous(), "rope: cos/sin must be fp32")
+    _req(cos.shape[0] >= S and cos.shape[1] == rot // 2, "rope: cos/sin must be [>=S, rot/2]")
+    check(_L(qkv).b200_rope_qk_inplace(ptr(qkv), ptr(cos), ptr(sin), B, S, nh, hd, rot, int(inverse), stream_ptr()), "b200_rope_qk_inplace")
+    return qkv
+
+
+# ----------------------------------------------------------------------------------------------------- Embedding
+def embedding_fwd(ids, table):
+    _req(ids.dtype == torch.int64 and ids.is_contiguous(), "embedding_fwd: ids must be contiguous int64")
+    _req(table.dtype == BF16 and table.is_contiguous(), "embedding_fwd: table must be contiguous bf16")
+    T, h = ids.numel(), table.shape[1]
+    out = torch.empty(T, h, dtype=BF16, device=table.device)
+    check(_L(table).b200_embedding_fwd(ptr(ids), ptr(table), ptr(out), T, h, table.shape[0], stream_ptr()), "b200_embedding_fwd")
+    return out
+
+
+def embedding3_fwd(ids0, table0, ids1=None, table1=None, ids2=None, table2=None):
+    T, h = ids0.numel(), table0.shape[1]
+    out = torch.empty(T, h, dtype=BF16, device=table0.device)
+    check(_L(table0).b200_embedding3_fwd(ptr(ids0), ptr(table0), ptr(ids1), ptr(table1), ptr(ids2), ptr(table2), ptr(out), T, h, stream_ptr()), "b200_embedding3_fwd")
+    return out
+
+
+def embedding_bwd(ids, dout, dtable):
+    _req(dout.dtype == BF16 and dout.is_contiguous() and dtable.dtype == F32, "embedding_bwd: dout bf16, dtable fp32")
+    T, h = ids.numel(), dtable.shape[1]
+    check(_L(dout).b200_embedding_bwd(ptr(ids), ptr(dout), ptr(dtable), T, h, dtable.shape[0], stream_ptr()), "b200_embedding_bwd")
+
+
+# ----------------------------------------------------------------------------------------------------- Cross entropy
+def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
+    """logits bf16 [T, ld] (overwritten by dlogits/n_valid when write_grad). Returns (loss scalar fp32 tensor, n_valid int tensor)."""
+    _req(logits.dtype == BF16 and logits.dim() == 2 and logits.stride(1) == 1, "cross_entropy: logits must be bf16 [T, ld]")
+    _req(labels.dtype == torch.int64 and labels.is_contiguous(), "cross_entropy: labels must be contiguous int64")
+    T, ld = logits.shape[0], logits.stride(0)
+    V = logits.shape[1] if V is None else V
+    lib = _L(logits)
+    dev = logits.device
+    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+    row_loss = torch.empty(T, dtype=F32, device=dev)
+    loss = torch.empty((), dtype=F32, device=dev)
+    s = stream_ptr()
+    check(lib.b200_count_valid(ptr(labels), T, ignore_index, ptr(n_valid), s), "b200_count_valid")
+    check(lib.b200_cross_entropy(ptr(logits), ptr(labels), ptr(row_loss), ptr(n_valid), T, V, ld, ignore_index, int(write_grad), s), "b200_cross_entropy")
+    check(lib.b200_mean_loss(ptr(row_loss), ptr(n_valid), T, ptr(loss), s), "b200_mean_loss")
+    return loss, n_valid
+
+
+# ----------------------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=False, bias=None, residual=None,
+         gelu=False, alpha=None, aux_out=None, dgelu_in=None):
+    """C[M,N] = epi(alpha * A·Bᵀ).  A is [M,K] (a_mn=False) or [K,M] (a_mn=True); B is [N,K] or [K,N] (b_mn=True)."""
+    _req(A.dtype == BF16 and B.dtype == BF16 and A.dim() == 2 and B.dim() == 2, "gemm: A,B must be 2-D bf16")
+    _req(A.stride(1) == 1 and B.stride(1) == 1, "gemm: A,B must have unit inner stride")
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    _req(K == Kb, f"gemm: reduction dims differ ({K} vs {Kb})")
+    if out is None:
+        _req(not accumulate, "gemm: accumulate needs out")
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    _req(out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (BF16, F32), "gemm: bad out")
+    a = GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_mn = ptr(A), A.stride(0), int(a_mn)
+    a.B, a.ldb, a.b_mn = ptr(B), B.stride(0), int(b_mn)
+    a.C, a.ldc, a.c_fp32, a.accumulate = ptr(out), out.stride(0), int(out.dtype == F32), int(accumulate)
+    if bias is not None:
+        _req(bias.dtype == F32 and bias.numel() == N and bias.is_contiguous(), "gemm: bias must be fp32 [N]")
+        a.bias = ptr(bias)
+    ldr = 0
+    if residual is not None:
+        _req(residual.dtype == BF16 and residual.shape == (M, N) and residual.stride(1) == 1, "gemm: bad residual")
+        a.residual, ldr = ptr(residual), residual.stride(0)
+    if dgelu_in is not None:
+        _req(dgelu_in.dtype == BF16 and dgelu_in.shape == (M, N) and dgelu_in.stride(1) == 1, "gemm: bad dgelu_in")
+        _req(residual is None or residual.stride(0) == dgelu_in.stride(0), "gemm: residual and dgelu_in must share a pitch")
+        a.dgelu_in, ldr = ptr(dgelu_in), dgelu_in.stride(0)
+    a.ldr = ldr
+    a.gelu = int(gelu)
+    if alpha is not None:
+        _req(alpha.dtype == F32 and alpha.numel() == 1, "gemm: alpha must be a device fp32 scalar")
+        a.alpha_dev = ptr(alpha)
+    if aux_out is not None:
+        _req(aux_out.dtype == BF16 and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0) and out.dtype == BF16, "gemm: aux_out must match a bf16 out")
+        a.aux_out = ptr(aux_out)
+    check(_L(A).b200_gemm_bf16(C.byref(a), stream_ptr()), "b200_gemm_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- Attention
+def _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale):
+    a = AttnArgs()
+    a.B, a.S, a.H, a.D = B, S, H, D
+    a.causal = int(causal)
+    a.scale = float(scale)
+    for t in (q, k, v):
+        _req(t.dtype == BF16 and t.dim() == 4 and t.shape == (B, S, H, D) and t.stride(3) == 1, "attention: q,k,v must be bf16 views [B,S,H,D] with unit inner stride")
+        _req(t.stride(0) == S * t.stride(1), "attention: batch stride must equal S * token stride")
+        _req(t.stride(1) == q.stride(1) and t.stride(2) == q.stride(2), "attention: q,k,v must share strides")
+    a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
+    a.qkv_row_stride, a.qkv_head_stride = q.stride(1), q.stride(2)
+    _req(o.dtype == BF16 and o.shape == (B, S, H, D) and o.stride(3) == 1 and o.stride(0) == S * o.stride(1), "attention: bad o")
+    a.o, a.o_row_stride, a.o_head_stride = ptr(o), o.stride(1), o.stride(2)
+    _req(lse.dtype == F32 and lse.shape == (B, H, S) and lse.is_contiguous(), "attention: lse must be fp32 [B,H,S]")
+    a.lse = ptr(lse)
+    return a
+
+
+def attention_fwd(q, k, v, causal, scale=None):
+    """q,k,v: bf16 views [B,S,H,D] (any token/head strides, e.g. slices of a packed qkv buffer). Returns (o [B,S,H,D], lse [B,H,S])."""
+    B, S, H, D = q.shape
+    scale = D ** -0.5 if scale is None else scale
+    o = torch.empty(B, S, H, D, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, S, dtype=F32, device=q.device)
+    a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
+    check(_L(q).b200_attention_fwd(C.byref(a), stream_ptr()), "b200_attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None):
+    """dq,dk,dv: bf16 views [B,S,H,D] sharing strides (e.g. slices of a packed dqkv buffer); written, not accumulated."""
+    B, S, H, D = q.shape
+    scale = D ** -0.5 if scale is None else scale
+    a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
+    _req(d_o.dtype == BF16 and d_o.shape == o.shape and d_o.stride() == o.stride(), "attention_bwd: dO must match O")
+    for t in (dq, dk, dv):
+        _req(t.dtype == BF16 and t.shape == (B, S, H, D) and t.stride(3) == 1 and t.stride(0) == S * t.stride(1), "attention_bwd: bad dq/dk/dv")
+        _req(t.stride(1) == dq.stride(1) and t.stride(2) == dq.stride(2), "attention_bwd: dq,dk,dv must share strides")
+    delta = torch.empty(B, H, S, dtype=F32, device=q.device)
+    a.d_o, a.delta = ptr(d_o), ptr(delta)
+    a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
+    a.dqkv_row_stride, a.dqkv_head_stride = dq.stride(1), dq.stride(2)
+    check(_L(q).b200_attention_bwd(C.byref(a), stream_ptr()), "b200_attention_bwd")
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------- Optimizer
+def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_group, groups, grad_scale=None, zero_grad=False):
+    n_chunks = chunk_start.numel()
+    arr = (AdamGroup * len(groups))()
+    for i, gdict in enumerate(groups):
+        arr[i].lr, arr[i].beta1, arr[i].beta2, arr[i].eps = gdict["lr"], gdict["beta1"], gdict["beta2"], gdict["eps"]
+        arr[i].weight_decay, arr[i].bias_corr1, arr[i].bias_corr2 = gdict["weight_decay"], gdict["bias_corr1"], gdict["bias_corr2"]
+        arr[i].adamw_mode = int(gdict["adamw_mode"])
+    check(_L(p).b200_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), int(state_base), ptr(chunk_start), ptr(chunk_len),
+                               ptr(chunk_group), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad), stream_ptr()), "b200_adam_step")
+
+
+def sumsq_(x, out):
+    """out (fp32 scalar tensor) += sum(x^2)."""
+    _req(x.dtype == F32 and x.is_contiguous() and out.dtype == F32, "sumsq: fp32 expected")
+    check(_L(x).b200_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()), "b200_sumsq")
+    return out
+
+
+def clip_coef(sumsq, max_norm):
+    norm = torch.empty((), dtype=F32, device=sumsq.device)
+    coef = torch.empty((), dtype=F32, device=sumsq.device)
+    check(_L(sumsq).b200_clip_coef(ptr(sumsq), float(max_norm), ptr(norm), ptr(coef), stream_ptr()), "b200_clip_coef")
+    return norm, coef
+
+
+def cast_f32_to_bf16(src, dst):
+    _req(src.dtype == F32 and dst.dtype == BF16 and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous(), "cast: bad tensors")
+    check(_L(src).b200_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "b200_cast_f32_to_bf16")
+    return dst
+
+
+def scale_f32_(x, scale_dev=None, scale_host=1.0):
+    _req(x.dtype == F32 and x.is_contiguous(), "scale_f32: contiguous fp32 expected")
+    check(_L(x).b200_scale_f32(ptr(x), x.numel(), ptr(scale_dev), float(scale_host), stream_ptr()), "b200_scale_f32")
+    return x
