@@ -382,6 +382,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const int h = blockIdx.y, b = blockIdx.z;
     const int r0 = blk * 128;  // first resident row (query row for dQ, key row for dK/dV)
     const int col0 = h * static_cast<int>(p.qkv_head_stride);
+    const int col0_do = h * static_cast<int>(p.o_head_stride);  // dO shares O's layout, not the packed qkv layout
     const int row_base = b * p.S;
     // streamed tile range
     int t_begin, t_end;
@@ -424,7 +425,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             mbar_expect_tx(r_full, 2 * L::R_BYTES);
             for (int c = 0; c < NSUB; ++c) {
                 tma_load_2d(sR1 + c * 16384, &tmR1, r_full, col0 + c * 64, row_base + r0);
-                tma_load_2d(sR2 + c * 16384, &tmR2, r_full, col0 + c * 64, row_base + r0);
+                tma_load_2d(sR2 + c * 16384, &tmR2, r_full, (DKV ? col0 : col0_do) + c * 64, row_base + r0);
             }
         }
         for (int t = 0; t < n_tiles; ++t) {
@@ -435,7 +436,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 const int row = row_base + (t_begin + t) * BT;
                 for (int c = 0; c < NSUB; ++c) {
                     tma_load_2d(sT1 + s * L::T_BYTES + c * 8192, &tmT1, &t_full[s], col0 + c * 64, row);
-                    tma_load_2d(sT2 + s * L::T_BYTES + c * 8192, &tmT2, &t_full[s], col0 + c * 64, row);
+                    tma_load_2d(sT2 + s * L::T_BYTES + c * 8192, &tmT2, &t_full[s], (DKV ? col0_do : col0) + c * 64, row);
                 }
             }
             __syncwarp();

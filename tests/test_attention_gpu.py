@@ -1,0 +1,98 @@
+"""tcgen05 flash attention (C ABI) vs an fp32 PyTorch statement of softmax(QK^T * scale [+causal]) V, outputs and
+gradients. Tolerance rel <= 2e-2 (bf16 operands, fp32 accumulate) as north_star states."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from multimodal_llm_pretraining_b200 import kernels as K  # noqa: E402
+
+BF16 = torch.bfloat16
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+
+
+def ref_attention(q, k, v, causal, scale):
+    # q,k,v fp32 [B,S,H,D]
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    s = (qh @ kh.transpose(-1, -2)) * scale
+    if causal:
+        S = q.shape[1]
+        mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+        s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = (p @ vh).permute(0, 2, 1, 3)
+    lse = torch.logsumexp(s, dim=-1)  # [B,H,S]
+    return o, lse
+
+
+CASES = [
+    # B, S, H, D, causal, packed
+    (2, 256, 2, 64, True, True),
+    (1, 512, 3, 64, False, True),
+    (2, 384, 2, 128, True, True),
+    (1, 256, 2, 128, False, False),
+    (2, 256, 2, 256, True, True),
+    (1, 640, 1, 256, True, True),
+    (1, 384, 2, 256, False, False),
+    (1, 200, 2, 64, True, True),     # ragged: S not a multiple of the tile
+    (1, 136, 1, 256, True, True),
+    (1, 2048, 2, 256, True, True),   # Pythia-1b head shape at full sequence length
+    (1, 2048, 2, 64, True, True),
+]
+
+
+def make_qkv(B, S, H, D, packed, dev, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if packed:  # GPT-NeoX layout [B,S,H,3,D]
+        buf = torch.randn(B, S, H, 3, D, generator=g).to(dev).to(BF16)
+        return buf, buf[:, :, :, 0], buf[:, :, :, 1], buf[:, :, :, 2]
+    q = torch.randn(B, S, H, D, generator=g).to(dev).to(BF16)
+    k = torch.randn(B, S, H, D, generator=g).to(dev).to(BF16)
+    v = torch.randn(B, S, H, D, generator=g).to(dev).to(BF16)
+    return None, q, k, v
+
+
+@pytest.mark.parametrize("B,S,H,D,causal,packed", CASES)
+def test_attention_fwd_bwd(dev, B, S, H, D, causal, packed):
+    _, q, k, v = make_qkv(B, S, H, D, packed, dev, seed=S + D)
+    scale = D ** -0.5
+    o, lse = K.attention_fwd(q, k, v, causal, scale)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    ro, rlse = ref_attention(qf, kf, vf, causal, scale)
+    assert torch.isfinite(o.float()).all()
+    e = rel_err(o, ro)
+    assert e <= 2e-2, f"O rel err {e:.3e}"
+    e = (lse - rlse).abs().max().item()
+    assert e <= 2e-2, f"LSE max abs err {e:.3e}"
+
+    g = torch.Generator(device="cpu").manual_seed(7)
+    d_o = torch.randn(B, S, H, D, generator=g).to(dev).to(BF16)
+    ro.backward(d_o.float())
+    if packed:
+        dbuf = torch.full((B, S, H, 3, D), float("nan"), device=dev, dtype=BF16)
+        dq, dk, dv = dbuf[:, :, :, 0], dbuf[:, :, :, 1], dbuf[:, :, :, 2]
+    else:
+        dq, dk, dv = (torch.full((B, S, H, D), float("nan"), device=dev, dtype=BF16) for _ in range(3))
+    K.attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale)
+    for name, got, ref in (("dQ", dq, qf.grad), ("dK", dk, kf.grad), ("dV", dv, vf.grad)):
+        assert torch.isfinite(got.float()).all(), f"{name} has non-finite values"
+        e = rel_err(got, ref)
+        assert e <= 2e-2, f"{name} rel err {e:.3e}"
+
+
+def test_attention_large_logits(dev):
+    # running-max path: growing scores force O rescales
+    B, S, H, D = 1, 512, 1, 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q = (torch.randn(B, S, H, D, generator=g) * 4).to(dev).to(BF16)
+    k = (torch.randn(B, S, H, D, generator=g) * 4).to(dev).to(BF16)
+    k = (k.float() * torch.linspace(0.1, 3.0, S, device=dev)[None, :, None, None]).to(BF16)
+    v = torch.randn(B, S, H, D, generator=g).to(dev).to(BF16)
+    o, lse = K.attention_fwd(q, k, v, False, D ** -0.5)
+    ro, rlse = ref_attention(q.float(), k.float(), v.float(), False, D ** -0.5)
+    assert rel_err(o, ro) <= 2e-2
+    assert ((lse - rlse).abs() / rlse.abs().clamp_min(1)).max().item() <= 1e-2
