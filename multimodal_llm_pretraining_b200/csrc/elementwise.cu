@@ -201,6 +201,55 @@ scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scal
         x[i] *= s;
 }
 
+
+// ----------------------------------------------------------------------------------------------- column sums (bias grads)
+// partial[rc][c] = sum over rows of chunk rc of x[r][c]; block = 32 column-lanes (8 cols each) x 8 row-lanes.
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int64_t ld, int rows_per_chunk,
+                      float* __restrict__ partial) {
+    __shared__ float sm[8][32][9];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + cx) * 8;
+    const int r_begin = blockIdx.y * rows_per_chunk;
+    const int r_end = min(rows, r_begin + rows_per_chunk);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (col < cols) {
+        for (int r = r_begin + ry; r < r_end; r += 8) {
+            const uint4 v = ld_nc_v4(x + static_cast<size_t>(r) * ld + col);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf2_to_f2(w[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[ry][cx][j] = acc[j];
+    __syncthreads();
+    if (ry == 0 && col < cols) {
+        float* out = partial + static_cast<size_t>(blockIdx.y) * cols + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += sm[k][cx][j];
+            out[j] = t;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float t = 0.f;
+    for (int p = 0; p < n_partial; ++p) t += partial[static_cast<size_t>(p) * cols + c];
+    out[c] += t;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -268,4 +317,24 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200
 extern "C" int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream) {
     scale_f32_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, scale_dev, scale_host);
     return check_launch("scale_f32");
+}
+
+extern "C" size_t b200_colsum_workspace_bytes(int cols) { return static_cast<size_t>(64) * cols * sizeof(float); }
+extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, void* workspace,
+                                size_t workspace_bytes, b200_stream_t stream) {
+    B200_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && aligned16(x), "colsum: cols/ld must be multiples of 8 and x 16B aligned");
+    B200_REQUIRE(workspace_bytes >= b200_colsum_workspace_bytes(cols), "colsum: workspace too small");
+    const int col_blocks = (cols + 255) / 256;
+    int chunks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+    if (chunks > 64) chunks = 64;
+    if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+    if (chunks < 1) chunks = 1;
+    const int rows_per_chunk = (rows + chunks - 1) / chunks;
+    chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    float* part = static_cast<float*>(workspace);
+    colsum_partial_kernel<<<dim3(col_blocks, chunks), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, ld, rows_per_chunk, part);
+    int rc = check_launch("colsum_partial");
+    if (rc) return rc;
+    colsum_finalize_kernel<<<(cols + 255) / 256, 256, 0, as_stream(stream)>>>(part, chunks, cols, out);
+    return check_launch("colsum_finalize");
 }

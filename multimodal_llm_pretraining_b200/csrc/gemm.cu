@@ -291,6 +291,13 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
                       uint32_t box_inner, uint32_t box_outer) {
     int rc = resolve_driver();
     if (rc) return rc;
+    // The driver entry point needs a current context on THIS thread; autograd's backward thread may only have had
+    // cudaSetDevice() called. cudaFree(0) binds the primary context (once per thread).
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(0);
+        ctx_bound = true;
+    }
     if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (pitch_elems * 2) % 16 != 0)
         return fail(-1, "tensor map: base must be 16B aligned and pitch a multiple of 8 elements (pitch=%llu)", (unsigned long long)pitch_elems);
     cuuint64_t dims[2] = {inner, outer};

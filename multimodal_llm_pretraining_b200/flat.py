@@ -1,0 +1,96 @@
+"""Flat parameter storage for the B200 modules.
+
+HBM layout (one contiguous buffer each, same offsets in all of them):
+    master : fp32   — the nn.Parameters are views into it (HF-compatible state_dict, torch optimizers work on it)
+    grad   : fp32   — the .grad of every parameter is a view into it; wgrad GEMMs accumulate straight into it
+    shadow : bf16   — what the tensor-core kernels read; rewritten by the fused Adam in the same pass that updates master
+Every parameter starts at a multiple of 64 elements (256 B fp32 / 128 B bf16) so TMA bases and vector accesses are aligned.
+A contiguous layout makes the optimizer one launch, the gradient norm one launch, and DDP / ZeRO-1 collectives plain
+slices of one buffer (bucket = a contiguous range, shard = a contiguous range).
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+ALIGN = 64
+
+
+class FlatParams:
+    def __init__(self, shapes: list[tuple[str, tuple[int, ...]]], device="cpu"):
+        self.names = [n for n, _ in shapes]
+        self.shapes = {n: tuple(s) for n, s in shapes}
+        self.offsets: dict[str, int] = {}
+        off = 0
+        for n, s in shapes:
+            self.offsets[n] = off
+            off += (math.prod(s) + ALIGN - 1) // ALIGN * ALIGN
+        # total padded to a multiple of 8 * ALIGN so it splits evenly into up to 8 aligned ZeRO shards
+        self.numel = (off + 8 * ALIGN - 1) // (8 * ALIGN) * (8 * ALIGN)
+        self.master = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=device)
+        self.shadow_version = -1
+        self.params: list[nn.Parameter] = []
+        self.pending_grad_scale: torch.Tensor | None = None  # clip coefficient folded into the next fused Adam step
+
+    # ---- views
+    def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        o, s = self.offsets[name], self.shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def range_of(self, names: list[str]) -> tuple[int, int]:
+        """[start, end) element range covering the (contiguous) parameters `names`, including alignment padding."""
+        starts = [self.offsets[n] for n in names]
+        ends = [self.offsets[n] + (math.prod(self.shapes[n]) + ALIGN - 1) // ALIGN * ALIGN for n in names]
+        return min(starts), max(ends)
+
+    def make_parameter(self, name: str) -> nn.Parameter:
+        p = nn.Parameter(self.view(self.master, name), requires_grad=True)
+        p.grad = self.view(self.grad, name)
+        p._b200_flat = (self, self.offsets[name], math.prod(self.shapes[name]))  # type: ignore[attr-defined]
+        self.params.append(p)
+        return p
+
+    def rebind(self, params: dict[str, nn.Parameter]) -> None:
+        for name, p in params.items():
+            p.data = self.view(self.master, name)
+            p.grad = self.view(self.grad, name)
+            p._b200_flat = (self, self.offsets[name], math.prod(self.shapes[name]))  # type: ignore[attr-defined]
+
+    def apply(self, fn) -> None:
+        """Move/cast the buffers (used by nn.Module._apply: .to(), .cuda()). The master stays fp32."""
+        new_master = fn(self.master)
+        if new_master.dtype != torch.float32:
+            raise TypeError("B200 modules keep fp32 master parameters; bf16 compute copies are managed internally "
+                            "(do not call .half()/.bfloat16() on the module)")
+        self.master = new_master.contiguous()
+        self.grad = self.grad.to(device=self.master.device)
+        self.shadow = self.shadow.to(device=self.master.device)
+        self.shadow_version = -1
+
+    # ---- shadow maintenance
+    def current_version(self) -> int:
+        # every in-place edit through torch (load_state_dict, torch optimizers, init) bumps the edited Parameter's
+        # version counter; the fused Adam writes through raw pointers and does not.
+        return sum(p._version for p in self.params)
+
+    def sync_shadow(self, force: bool = False) -> None:
+        """Refresh the bf16 compute copy if the fp32 master was modified through torch (load_state_dict, a torch
+        optimizer, manual edits). The fused Adam keeps both in step without bumping any version counter."""
+        v = self.current_version()
+        if force or v != self.shadow_version:
+            if self.master.is_cuda:
+                from . import kernels as K
+
+                K.cast_f32_to_bf16(self.master, self.shadow)
+            else:
+                self.shadow.copy_(self.master)
+            self.shadow_version = v
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        self.pending_grad_scale = None

@@ -136,6 +136,16 @@ def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
     return loss, n_valid
 
 
+def colsum_(x, out):
+    """out[c] (fp32) += sum_r x[r, c] for bf16 x [rows, cols]."""
+    _req(x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.numel() == x.shape[1], "colsum: bad tensors")
+    lib = _L(x)
+    rows, cols = x.shape
+    ws = _workspace(x.device, lib.b200_colsum_workspace_bytes(cols))
+    check(lib.b200_colsum_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), ptr(ws), ws.numel(), stream_ptr()), "b200_colsum_bf16")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=False, bias=None, residual=None,
          gelu=False, alpha=None, aux_out=None, dgelu_in=None):

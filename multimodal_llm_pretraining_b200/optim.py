@@ -1,0 +1,176 @@
+"""B200Adam / B200AdamW: fused multi-tensor Adam over the flat parameter store (one kernel launch per step).
+
+Drop-in for the optimizer class hand-off of the reference (`BaseModelClass.optimizer`, src/models/__init__.py:116-126;
+constructed by HF Trainer as `cls(param_groups, **kwargs)`, HF:trainer.py:1157-1198): same constructor signature and
+semantics as torch.optim.Adam (L2-coupled weight decay — what src/models/pythia.py:43-45 selects, DeepSpeed
+`adam_w_mode: False`, src/train.py:157-167) and torch.optim.AdamW (decoupled).  `.param_groups` stay live so that LR
+schedulers mutate `group["lr"]` as usual; `.state_dict()` / `.load_state_dict()` carry step, exp_avg, exp_avg_sq.
+
+ZeRO-1: pass `shard=(start, end)` (element range of the flat buffer this rank owns): moments are allocated for the
+shard only and the kernel touches only chunks inside it.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import torch
+
+from . import kernels as K
+from .flat import FlatParams
+
+CHUNK = 65536
+
+
+class B200Adam(torch.optim.Optimizer):
+    adamw_mode = False
+
+    def __init__(self, params, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, shard: tuple[int, int] | None = None, zero_grad_in_step: bool = False, **_ignored):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameters")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        flats = set()
+        for g in self.param_groups:
+            for p in g["params"]:
+                info = getattr(p, "_b200_flat", None)
+                if info is None:
+                    raise TypeError("B200Adam only optimises parameters of B200 modules (flat fp32 store); "
+                                    "use torch.optim.Adam for foreign parameters")
+                flats.add(id(info[0]))
+                self._flat = info[0]
+        if len(flats) != 1:
+            raise ValueError("B200Adam expects all parameters to come from one B200 module")
+        if len(self.param_groups) > 8:
+            raise ValueError("at most 8 param groups are supported by the fused kernel")
+        self._shard = shard
+        self._zero_grad_in_step = zero_grad_in_step
+        self._step = 0
+        self._built_for = None
+        self._m = self._v = None
+
+    # ------------------------------------------------------------------ chunk table / state
+    def _build(self) -> None:
+        f: FlatParams = self._flat
+        dev = f.master.device
+        lo, hi = self._shard if self._shard is not None else (0, f.numel)
+        starts, lens, grps = [], [], []
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                _, off, n = p._b200_flat
+                a, b = max(off, lo), min(off + n, hi)
+                c = a
+                while c < b:
+                    ln = min(CHUNK, b - c)
+                    starts.append(c), lens.append(ln), grps.append(gi)
+                    c += ln
+        self._chunk_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+        self._chunk_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+        self._chunk_group = torch.tensor(grps, dtype=torch.int32, device=dev)
+        self._state_base = lo
+        if self._m is None or self._m.numel() != hi - lo or self._m.device != dev:
+            m_old, v_old = self._m, self._v
+            self._m = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
+            self._v = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
+            if m_old is not None and m_old.numel() == hi - lo:
+                self._m.copy_(m_old), self._v.copy_(v_old)
+        self._built_for = (dev, f.master.data_ptr(), lo, hi)
+
+    def _ensure_built(self) -> None:
+        f = self._flat
+        lo, hi = self._shard if self._shard is not None else (0, f.numel)
+        if self._built_for != (f.master.device, f.master.data_ptr(), lo, hi):
+            self._build()
+
+    # ------------------------------------------------------------------ torch.optim API
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: torch.Tensor | None = None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        f = self._flat
+        if not f.master.is_cuda:
+            raise RuntimeError("B200Adam needs the module on a CUDA (sm_100a) device; there is no CPU fallback")
+        self._ensure_built()
+        self._step += 1
+        t = self._step
+        groups = []
+        for g in self.param_groups:
+            b1, b2 = g["betas"]
+            groups.append(dict(lr=float(g["lr"]), beta1=b1, beta2=b2, eps=g["eps"], weight_decay=g["weight_decay"],
+                               bias_corr1=1.0 - b1 ** t, bias_corr2=1.0 - b2 ** t, adamw_mode=self.adamw_mode))
+        if grad_scale is None:
+            grad_scale = f.pending_grad_scale
+        f.pending_grad_scale = None
+        f.sync_shadow()  # no-op unless the master was edited through torch since the last step
+        K.adam_step(f.master, f.grad, self._m, self._v, f.shadow, self._state_base, self._chunk_start, self._chunk_len,
+                    self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step)
+        return loss
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self._flat.zero_grad()
+
+    # ------------------------------------------------------------------ (de)serialisation
+    def state_dict(self) -> dict[str, Any]:
+        return {
+            "step": self._step,
+            "shard": self._shard,
+            "exp_avg": None if self._m is None else self._m.detach().cpu(),
+            "exp_avg_sq": None if self._v is None else self._v.detach().cpu(),
+            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+        }
+
+    def load_state_dict(self, sd: dict[str, Any]) -> None:
+        self._step = int(sd["step"])
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update(saved)
+        if sd.get("exp_avg") is not None:
+            self._ensure_built()
+            self._m.copy_(sd["exp_avg"])
+            self._v.copy_(sd["exp_avg_sq"])
+
+
+class B200AdamW(B200Adam):
+    adamw_mode = True
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, **kw):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------- LR schedules
+def cosine_with_min_lr_lambda(step: int, *, num_warmup_steps: int, num_training_steps: int, num_cycles: float = 0.5,
+                              min_lr_rate: float = 0.0) -> float:
+    """HF:optimization.py:324-334 (_get_cosine_with_min_lr_schedule_with_warmup_lr_lambda)."""
+    if step < num_warmup_steps:
+        return float(step) / float(max(1, num_warmup_steps))
+    progress = float(step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+    factor = 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress))
+    factor = factor * (1 - min_lr_rate) + min_lr_rate
+    return max(0, factor)
+
+
+def linear_lambda(step: int, *, num_warmup_steps: int, num_training_steps: int) -> float:
+    """HF:optimization.py:101-104 (_get_linear_schedule_with_warmup_lr_lambda)."""
+    if step < num_warmup_steps:
+        return float(step) / float(max(1, num_warmup_steps))
+    return max(0.0, float(num_training_steps - step) / float(max(1, num_training_steps - num_warmup_steps)))
+
+
+def get_scheduler(name: str, optimizer: torch.optim.Optimizer, num_warmup_steps: int, num_training_steps: int,
+                  scheduler_specific_kwargs: dict | None = None) -> torch.optim.lr_scheduler.LambdaLR:
+    """The two schedules the in-scope model classes use (src/models/pythia.py:69-78, src/models/roberta.py:44-50)."""
+    from functools import partial
+
+    kw = dict(scheduler_specific_kwargs or {})
+    name = getattr(name, "value", name)
+    if name == "cosine_with_min_lr":
+        fn = partial(cosine_with_min_lr_lambda, num_warmup_steps=num_warmup_steps, num_training_steps=num_training_steps,
+                     num_cycles=kw.get("num_cycles", 0.5), min_lr_rate=kw.get("min_lr_rate", 0.0))
+    elif name == "linear":
+        fn = partial(linear_lambda, num_warmup_steps=num_warmup_steps, num_training_steps=num_training_steps)
+    else:
+        raise NotImplementedError(f"scheduler {name!r} is not used by the in-scope model classes")
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, fn)

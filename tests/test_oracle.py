@@ -1,0 +1,82 @@
+"""CPU tests (run with -m "not gpu"): the oracle restatement is pinned against golden vectors produced by the real
+reference call path (transformers.GPTNeoXForCausalLM + torch.optim.Adam; tests/golden/make_golden.py)."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import neox_oracle as O  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden" / "neox_tiny.pt"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, map_location="cpu", weights_only=False)
+
+
+def test_oracle_loss_and_logits_match_hf_golden(gold):
+    P = {k: v.clone() for k, v in gold["state_dict"].items()}
+    ids = gold["batches"][0]
+    logits = O.neox_logits(P, ids, gold["cfg"])
+    assert torch.allclose(logits[:, :4, :8], gold["logits0_slice"], atol=2e-5, rtol=1e-4)
+    loss = O.causal_lm_loss(logits, ids)
+    assert abs(loss.item() - gold["loss0"]) < 2e-5
+
+
+def test_oracle_grads_match_hf_golden(gold):
+    P = {k: v.clone() for k, v in gold["state_dict"].items()}
+    ids = gold["batches"][0]
+    _, grads = O.neox_loss_and_grads(P, ids, ids, gold["cfg"])
+    for k, n in gold["grad_norms"].items():
+        assert abs(grads[k].norm().item() - n) <= 1e-4 * max(n, 1e-3), k
+    for k, g in gold["grads"].items():
+        assert torch.allclose(grads[k], g, atol=1e-6, rtol=1e-3), k
+
+
+def test_oracle_adam_steps_match_torch_golden(gold):
+    P = {k: v.clone() for k, v in gold["state_dict"].items()}
+    losses = O.train_steps(P, gold["batches"], gold["cfg"], lr=6e-4, betas=(0.9, 0.95), eps=1e-8, max_grad_norm=1.0,
+                           warmup=0, total_steps=1)
+    for a, b in zip(losses, gold["losses"]):
+        assert abs(a - b) < 5e-5, (losses, gold["losses"])
+    for k, v in gold["params_after3"].items():
+        assert torch.allclose(P[k], v, atol=2e-6, rtol=1e-4), k
+    for k, n in gold["param_norms_after3"].items():
+        assert abs(P[k].norm().item() - n) <= 1e-5 * max(n, 1e-3), k
+
+
+def test_dead_last_token_identity(gold):
+    """model(ids)[loss] with HF's internal shift == model(ids[:, :-1]) against ids[:, 1:]."""
+    P = {k: v.double() for k, v in gold["state_dict"].items()}
+    ids = gold["batches"][1]
+    full = O.neox_loss(P, ids, ids, gold["cfg"])
+    logits = O.neox_logits(P, ids[:, :-1], gold["cfg"])
+    short = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), ids[:, 1:].reshape(-1))
+    assert abs(full.item() - short.item()) < 1e-6  # HF upcasts the loss path to fp32
+
+
+def test_oracle_matches_live_hf_when_available(gold):
+    tr = pytest.importorskip("transformers")
+    cfg = tr.GPTNeoXConfig(**gold["cfg"], attn_implementation="eager")
+    m = tr.GPTNeoXForCausalLM(cfg).float()
+    m.load_state_dict(gold["state_dict"], strict=False)
+    ids = gold["batches"][2]
+    ref = m(input_ids=ids, labels=ids).loss
+    got = O.neox_loss({k: v.clone() for k, v in gold["state_dict"].items()}, ids, ids, gold["cfg"])
+    assert abs(ref.item() - got.item()) < 2e-5
+
+
+def test_schedule_matches_hf_formula():
+    # Pythia: warmup 1430 of 143000 steps, min_lr_rate 0.1 (src/models/pythia.py:69-78)
+    assert O.cosine_with_min_lr(0, 1430, 143000, 0.1) == 0.0
+    assert abs(O.cosine_with_min_lr(715, 1430, 143000, 0.1) - 0.5) < 1e-12
+    assert abs(O.cosine_with_min_lr(1430, 1430, 143000, 0.1) - 1.0) < 1e-12
+    assert abs(O.cosine_with_min_lr(143000, 1430, 143000, 0.1) - 0.1) < 1e-12
+    from multimodal_llm_pretraining_b200.optim import cosine_with_min_lr_lambda
+    for s in (0, 10, 1429, 1430, 50000, 143000):
+        assert abs(cosine_with_min_lr_lambda(s, num_warmup_steps=1430, num_training_steps=143000, min_lr_rate=0.1)
+                   - O.cosine_with_min_lr(s, 1430, 143000, 0.1)) < 1e-12
