@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 3
+#define B200PT_ABI_VERSION 4
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
@@ -152,8 +152,9 @@ int b200_attention_bwd(const b200_attn_args* args, b200_stream_t stream);
 /* ---------------------------------------------------------------- Optimizer (fused multi-tensor Adam / AdamW)
  * Replaces torch.optim.Adam foreach path and DeepSpeed FusedAdam (src/models/pythia.py:43-67, src/train.py:157-167).
  * All parameters live in one flat fp32 buffer; `chunks` partition the part this rank updates into pieces that each
- * belong to one param group. p/g are indexed by absolute element offset; m/v by (offset - state_base) so that a
- * ZeRO-1 shard can keep only its slice of the moments.
+ * belong to one param group. p/g are indexed by absolute element offset; m/v by chunk_state[c] + i when chunk_state is
+ * given (a ZeRO-1 rank keeps only the moments of the slices it owns, packed back to back), else by
+ * (offset - state_base).
  *   adamw_mode = 0: L2 (torch.optim.Adam):  g += wd*p          adamw_mode = 1: decoupled (p *= 1 - lr*wd)
  *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
  * grad_scale_dev (nullable): device fp32 scalar multiplied into every gradient first (clip coefficient / unscale).
@@ -164,9 +165,9 @@ typedef struct b200_adam_group {
 } b200_adam_group;
 #define B200_ADAM_MAX_GROUPS 8
 int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
-                   const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks,
-                   const b200_adam_group* groups, int n_groups, const float* grad_scale_dev, int zero_grad,
-                   b200_stream_t stream);
+                   const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group,
+                   const int64_t* chunk_state, int n_chunks, const b200_adam_group* groups, int n_groups,
+                   const float* grad_scale_dev, int zero_grad, b200_stream_t stream);
 /* out[0] += sum(x[i]^2) (fp32 atomics over per-block partials). */
 int b200_sumsq(const float* x, size_t n, float* out, b200_stream_t stream);
 /* norm_out = sqrt(sumsq); coef_out = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_ semantics);

@@ -14,7 +14,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200pt.so"
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -78,7 +78,7 @@ SIGNATURES = {
     "b200_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b200_attention_fwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
     "b200_attention_bwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
-    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p]),
+    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p]),
     "b200_sumsq": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "b200_clip_coef": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "b200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -30,17 +30,19 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ p16, int64_t state_base, const int64_t* __restrict__ chunk_start,
-            const int32_t* __restrict__ chunk_len, const int32_t* __restrict__ chunk_group, const AdamGroups groups,
-            const float* __restrict__ grad_scale, int zero_grad) {
+            const int32_t* __restrict__ chunk_len, const int32_t* __restrict__ chunk_group,
+            const int64_t* __restrict__ chunk_state, const AdamGroups groups, const float* __restrict__ grad_scale,
+            int zero_grad) {
     const int64_t start = chunk_start[blockIdx.x];
     const int len = chunk_len[blockIdx.x];
     const b200_adam_group h = groups.g[chunk_group[blockIdx.x]];
     const float gs = grad_scale ? *grad_scale : 1.0f;
     float* pp = p + start;
     float* gp = g + start;
-    float* mp = m + (start - state_base);
-    float* vp = v + (start - state_base);
-    const bool vec_ok = ((start & 3) == 0) && (((start - state_base) & 3) == 0);
+    const int64_t soff = chunk_state ? chunk_state[blockIdx.x] : (start - state_base);
+    float* mp = m + soff;
+    float* vp = v + soff;
+    const bool vec_ok = ((start & 3) == 0) && ((soff & 3) == 0);
     const int n4 = vec_ok ? len / 4 : 0;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
         float4 P = reinterpret_cast<float4*>(pp)[i];
@@ -102,14 +104,14 @@ using namespace b200;
 
 extern "C" int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
                               const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group,
-                              int n_chunks, const b200_adam_group* groups, int n_groups, const float* grad_scale_dev,
-                              int zero_grad, b200_stream_t stream) {
+                              const int64_t* chunk_state, int n_chunks, const b200_adam_group* groups, int n_groups,
+                              const float* grad_scale_dev, int zero_grad, b200_stream_t stream) {
     B200_REQUIRE(n_groups > 0 && n_groups <= B200_ADAM_MAX_GROUPS, "adam_step: n_groups %d out of range", n_groups);
     if (n_chunks == 0) return 0;
     AdamGroups gs;
     for (int i = 0; i < n_groups; ++i) gs.g[i] = groups[i];
     adam_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), state_base,
-                                                         chunk_start, chunk_len, chunk_group, gs, grad_scale_dev, zero_grad);
+                                                         chunk_start, chunk_len, chunk_group, chunk_state, gs, grad_scale_dev, zero_grad);
     return check_launch("adam_step");
 }
 extern "C" int b200_sumsq(const float* x, size_t n, float* out, b200_stream_t stream) {

@@ -1,0 +1,171 @@
+"""Data-parallel step engine: what HF Trainer + accelerate (DDP) / DeepSpeed (ZeRO-1) do for the benchmarked configs,
+on top of the flat parameter store (src/train.py:126-171 selects the strategy declaratively in the reference;
+src/benchmarking/utils.py:61-80 drives it).
+
+One process per GPU; `torch.distributed` (NCCL over NVLink 5 / NVSwitch) is the plumbing. The path shards naturally:
+every rank runs independent micro-batches; the only exchange is per optimizer step.
+
+  strategy "none"  : single GPU.
+  strategy "ddp"   : per-layer buckets of the flat fp32 grad buffer are all-reduced (AVG) on a side stream as soon as
+                     the layer's backward has produced them (last micro-batch of the accumulation window only), then
+                     every rank runs the replicated fused Adam.
+  strategy "zero1" : the same buckets are reduce-scattered (AVG) in place — rank r keeps slice r of every bucket —
+                     local sum-of-squares + one scalar all-reduce give the global grad norm, the fused Adam updates
+                     only the owned slices (moments exist only for them: 8 B/param/W), then the fp32 master slices are
+                     all-gathered in place and the bf16 compute copy is refreshed with one cast pass.
+
+`CommPlan` holds the pure bucket/ownership arithmetic and the collective calls so that it can be exercised with gloo on
+CPU tensors (tests/test_engine_cpu.py, world_size 2).
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+class CommPlan:
+    """Buckets are [start, end) element ranges of the flat buffers (multiples of 64 elements)."""
+
+    def __init__(self, buckets: list[tuple[int, int]], world_size: int, rank: int, group=None):
+        self.buckets = sorted(buckets)
+        self.W, self.rank, self.group = world_size, rank, group
+        for s, e in self.buckets:
+            if (e - s) % (world_size * 4) != 0:
+                raise ValueError(f"bucket [{s},{e}) is not divisible into {world_size} 16-byte-aligned slices")
+
+    def owned_slice(self, bucket: tuple[int, int], rank: int | None = None) -> tuple[int, int]:
+        s, e = bucket
+        r = self.rank if rank is None else rank
+        n = (e - s) // self.W
+        return s + r * n, s + (r + 1) * n
+
+    def owned_ranges(self, rank: int | None = None) -> list[tuple[int, int]]:
+        return [self.owned_slice(b, rank) for b in self.buckets]
+
+    def bucket_of(self, start: int, end: int) -> tuple[int, int]:
+        for b in self.buckets:
+            if b[0] == start and b[1] == end:
+                return b
+        raise KeyError((start, end))
+
+    # ---- collectives on one bucket of a flat tensor
+    def _gloo(self) -> bool:
+        return dist.get_backend(self.group) == "gloo"
+
+    def all_reduce_avg(self, flat: torch.Tensor, bucket: tuple[int, int]) -> None:
+        t = flat[bucket[0]:bucket[1]]
+        if self._gloo():  # gloo has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.W)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+
+    def reduce_scatter_avg(self, flat: torch.Tensor, bucket: tuple[int, int]) -> None:
+        """In place: afterwards flat[owned_slice(bucket)] holds the mean over ranks; other slices are undefined."""
+        t = flat[bucket[0]:bucket[1]]
+        lo, hi = self.owned_slice(bucket)
+        if self._gloo():  # test backend: emulate with all-reduce
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.W)
+        else:
+            dist.reduce_scatter_tensor(flat[lo:hi], t, op=dist.ReduceOp.AVG, group=self.group)
+
+    def all_gather(self, flat: torch.Tensor, bucket: tuple[int, int]) -> None:
+        """In place: every rank contributes its owned slice of the bucket."""
+        t = flat[bucket[0]:bucket[1]]
+        lo, hi = self.owned_slice(bucket)
+        if self._gloo():
+            parts = [torch.empty(hi - lo, dtype=flat.dtype, device=flat.device) for _ in range(self.W)]
+            dist.all_gather(parts, flat[lo:hi].clone(), group=self.group)
+            for r, p_ in enumerate(parts):
+                a, b = self.owned_slice(bucket, r)
+                flat[a:b].copy_(p_)
+        else:
+            dist.all_gather_into_tensor(t, flat[lo:hi], group=self.group)
+
+    def all_reduce_sum_scalar(self, x: torch.Tensor) -> None:
+        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class TrainEngine:
+    """manual_training_step / manual_optimization_step of the reference harness (src/benchmarking/utils.py:61-80) for a
+    B200 module + B200Adam, with DDP or ZeRO-1 over the flat buffers."""
+
+    def __init__(self, model, optimizer, scheduler=None, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
+                 strategy: str = "none", group=None):
+        self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
+        self.max_grad_norm = max_grad_norm
+        self.ga = gradient_accumulation_steps
+        self.strategy = strategy
+        self.flat = model.flat
+        self.micro = 0
+        self.plan: CommPlan | None = None
+        self.comm_stream = None
+        self.last_grad_norm = None
+        if strategy not in ("none", "ddp", "zero1"):
+            raise ValueError(strategy)
+        if strategy != "none":
+            if not dist.is_initialized():
+                raise RuntimeError("strategy %r needs an initialised torch.distributed process group" % strategy)
+            W, r = dist.get_world_size(group), dist.get_rank(group)
+            self.plan = CommPlan(model.comm_buckets(), W, r, group)
+            self.comm_stream = torch.cuda.Stream()
+            if strategy == "zero1":
+                optimizer.set_shard(self.plan.owned_ranges())
+            # identical initial parameters everywhere (rank 0 wins), like DDP's constructor broadcast
+            dist.broadcast(self.flat.master, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self.flat.sync_shadow(force=True)
+
+    # ------------------------------------------------------------------ fwd + bwd of one micro-batch
+    def _on_grads_ready(self, start: int, end: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            b = self.plan.bucket_of(start, end)
+            if self.strategy == "ddp":
+                self.plan.all_reduce_avg(self.flat.grad, b)
+            else:
+                self.plan.reduce_scatter_avg(self.flat.grad, b)
+
+    def manual_training_step(self, inputs: dict) -> torch.Tensor:
+        """One micro-batch forward + backward with gradients ACCUMULATED; the loss is divided by the accumulation count
+        before backward (HF:trainer.py:1925-1927). Returns the (undivided) loss as a device scalar."""
+        boundary = (self.micro + 1) % self.ga == 0
+        self.model.grad_ready_hook = self._on_grads_ready if (self.plan is not None and boundary) else None
+        out = self.model(**inputs)
+        loss = out["loss"]
+        (loss / self.ga if self.ga > 1 else loss).backward()
+        self.micro += 1
+        return loss.detach()
+
+    # ------------------------------------------------------------------ optimizer step
+    def manual_optimization_step(self) -> None:
+        """clip (max_grad_norm > 0) -> optimizer.step -> lr_scheduler.step -> zero_grad (src/benchmarking/utils.py:65-80)."""
+        from . import kernels as K
+
+        f = self.flat
+        if self.plan is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            sumsq = torch.zeros((), dtype=torch.float32, device=f.grad.device)
+            if self.strategy == "zero1":
+                for lo, hi in self.plan.owned_ranges():
+                    K.sumsq_(f.grad[lo:hi], sumsq)
+                self.plan.all_reduce_sum_scalar(sumsq)
+            else:
+                K.sumsq_(f.grad, sumsq)
+            norm, coef = K.clip_coef(sumsq, self.max_grad_norm)
+            f.pending_grad_scale = coef
+            self.last_grad_norm = norm
+        self.optimizer.step()
+        if self.strategy == "zero1":
+            for b in self.plan.buckets:
+                self.plan.all_gather(f.master, b)
+            K.cast_f32_to_bf16(f.master, f.shadow)
+        if self.scheduler is not None:
+            self.scheduler.step()
+        self.model.zero_grad()

@@ -17,6 +17,16 @@ from ._lib import AdamGroup, AttnArgs, GemmArgs, check, ptr, stream_ptr
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# number of libb200pt kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+# optional GEMM profiler: a list that receives (flops, start_event, end_event) per GEMM call (bench.py roofline pass)
+GEMM_PROFILE: list | None = None
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _L(t: torch.Tensor):
     return _lib.lib_for(t.device)
@@ -39,6 +49,7 @@ def layernorm_fwd(x, gamma, beta, eps, gamma2=None, beta2=None):
     rstd = torch.empty(rows, dtype=F32, device=x.device)
     check(_L(x).b200_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(gamma2), ptr(beta2), ptr(y2), ptr(mean),
                                    ptr(rstd), rows, cols, float(eps), stream_ptr()), "b200_layernorm_fwd")
+    _count(1)
     return y, y2, mean, rstd
 
 
@@ -67,6 +78,7 @@ def layernorm_bwd(x, mean, rstd, gamma, dy, dgamma, dbeta, gamma2=None, dy2=None
     check(lib.b200_layernorm_bwd(ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dy), ptr(gamma2), ptr(dy2), ptr(dres),
                                  ptr(dx), ptr(dgamma), ptr(dbeta), ptr(dgamma2), ptr(dbeta2), ptr(ws), ws.numel(), rows,
                                  cols, stream_ptr()), "b200_layernorm_bwd")
+    _count(2)
     return dx
 
 
@@ -75,6 +87,7 @@ def gelu_fwd(x):
     _req(x.dtype == BF16 and x.is_contiguous(), "gelu_fwd: contiguous bf16 expected")
     y = torch.empty_like(x)
     check(_L(x).b200_gelu_fwd(ptr(x), ptr(y), x.numel(), stream_ptr()), "b200_gelu_fwd")
+    _count(1)
     return y
 
 
@@ -82,6 +95,7 @@ def gelu_bwd(x, dy):
     _req(x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous(), "gelu_bwd: contiguous bf16 expected")
     dx = torch.empty_like(x)
     check(_L(x).b200_gelu_bwd(ptr(x), ptr(dy), ptr(dx), x.numel(), stream_ptr()), "b200_gelu_bwd")
+    _count(1)
     return dx
 
 
@@ -91,6 +105,7 @@ def rope_qk_inplace(qkv, cos, sin, B, S, nh, hd, rot, inverse=False):
     _req(cos.dtype == F32 and sin.dtype == F32 and cos.is_contiguous() and sin.is_contiguous(), "rope: cos/sin must be fp32")
     _req(cos.shape[0] >= S and cos.shape[1] == rot // 2, "rope: cos/sin must be [>=S, rot/2]")
     check(_L(qkv).b200_rope_qk_inplace(ptr(qkv), ptr(cos), ptr(sin), B, S, nh, hd, rot, int(inverse), stream_ptr()), "b200_rope_qk_inplace")
+    _count(1)
     return qkv
 
 
@@ -101,6 +116,7 @@ def embedding_fwd(ids, table):
     T, h = ids.numel(), table.shape[1]
     out = torch.empty(T, h, dtype=BF16, device=table.device)
     check(_L(table).b200_embedding_fwd(ptr(ids), ptr(table), ptr(out), T, h, table.shape[0], stream_ptr()), "b200_embedding_fwd")
+    _count(1)
     return out
 
 
@@ -108,6 +124,7 @@ def embedding3_fwd(ids0, table0, ids1=None, table1=None, ids2=None, table2=None)
     T, h = ids0.numel(), table0.shape[1]
     out = torch.empty(T, h, dtype=BF16, device=table0.device)
     check(_L(table0).b200_embedding3_fwd(ptr(ids0), ptr(table0), ptr(ids1), ptr(table1), ptr(ids2), ptr(table2), ptr(out), T, h, stream_ptr()), "b200_embedding3_fwd")
+    _count(1)
     return out
 
 
@@ -115,6 +132,7 @@ def embedding_bwd(ids, dout, dtable):
     _req(dout.dtype == BF16 and dout.is_contiguous() and dtable.dtype == F32, "embedding_bwd: dout bf16, dtable fp32")
     T, h = ids.numel(), dtable.shape[1]
     check(_L(dout).b200_embedding_bwd(ptr(ids), ptr(dout), ptr(dtable), T, h, dtable.shape[0], stream_ptr()), "b200_embedding_bwd")
+    _count(1)
 
 
 # ----------------------------------------------------------------------------------------------------- Cross entropy
@@ -131,8 +149,11 @@ def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
     loss = torch.empty((), dtype=F32, device=dev)
     s = stream_ptr()
     check(lib.b200_count_valid(ptr(labels), T, ignore_index, ptr(n_valid), s), "b200_count_valid")
+    _count(1)
     check(lib.b200_cross_entropy(ptr(logits), ptr(labels), ptr(row_loss), ptr(n_valid), T, V, ld, ignore_index, int(write_grad), s), "b200_cross_entropy")
+    _count(1)
     check(lib.b200_mean_loss(ptr(row_loss), ptr(n_valid), T, ptr(loss), s), "b200_mean_loss")
+    _count(1)
     return loss, n_valid
 
 
@@ -143,6 +164,7 @@ def colsum_(x, out):
     rows, cols = x.shape
     ws = _workspace(x.device, lib.b200_colsum_workspace_bytes(cols))
     check(lib.b200_colsum_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), ptr(ws), ws.numel(), stream_ptr()), "b200_colsum_bf16")
+    _count(2)
     return out
 
 
@@ -189,7 +211,15 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=F
     if aux_out is not None:
         _req(aux_out.dtype == BF16 and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0) and out.dtype == BF16, "gemm: aux_out must match a bf16 out")
         a.aux_out = ptr(aux_out)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_L(A).b200_gemm_bf16(C.byref(a), stream_ptr()), "b200_gemm_bf16")
+    _count(1)
+    if prof is not None:
+        e1.record()
+        prof.append((2.0 * M * N * K, e0, e1))
     return out
 
 
@@ -220,6 +250,7 @@ def attention_fwd(q, k, v, causal, scale=None):
     lse = torch.empty(B, H, S, dtype=F32, device=q.device)
     a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
     check(_L(q).b200_attention_fwd(C.byref(a), stream_ptr()), "b200_attention_fwd")
+    _count(1)
     return o, lse
 
 
@@ -237,11 +268,13 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None):
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
     a.dqkv_row_stride, a.dqkv_head_stride = dq.stride(1), dq.stride(2)
     check(_L(q).b200_attention_bwd(C.byref(a), stream_ptr()), "b200_attention_bwd")
+    _count(3)
     return dq, dk, dv
 
 
 # ----------------------------------------------------------------------------------------------------- Optimizer
-def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_group, groups, grad_scale=None, zero_grad=False):
+def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_group, groups, grad_scale=None, zero_grad=False,
+              chunk_state=None):
     n_chunks = chunk_start.numel()
     arr = (AdamGroup * len(groups))()
     for i, gdict in enumerate(groups):
@@ -249,13 +282,15 @@ def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_grou
         arr[i].weight_decay, arr[i].bias_corr1, arr[i].bias_corr2 = gdict["weight_decay"], gdict["bias_corr1"], gdict["bias_corr2"]
         arr[i].adamw_mode = int(gdict["adamw_mode"])
     check(_L(p).b200_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), int(state_base), ptr(chunk_start), ptr(chunk_len),
-                               ptr(chunk_group), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad), stream_ptr()), "b200_adam_step")
+                               ptr(chunk_group), ptr(chunk_state), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad), stream_ptr()), "b200_adam_step")
+    _count(1)
 
 
 def sumsq_(x, out):
     """out (fp32 scalar tensor) += sum(x^2)."""
     _req(x.dtype == F32 and x.is_contiguous() and out.dtype == F32, "sumsq: fp32 expected")
     check(_L(x).b200_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()), "b200_sumsq")
+    _count(1)
     return out
 
 
@@ -263,16 +298,19 @@ def clip_coef(sumsq, max_norm):
     norm = torch.empty((), dtype=F32, device=sumsq.device)
     coef = torch.empty((), dtype=F32, device=sumsq.device)
     check(_L(sumsq).b200_clip_coef(ptr(sumsq), float(max_norm), ptr(norm), ptr(coef), stream_ptr()), "b200_clip_coef")
+    _count(1)
     return norm, coef
 
 
 def cast_f32_to_bf16(src, dst):
     _req(src.dtype == F32 and dst.dtype == BF16 and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous(), "cast: bad tensors")
     check(_L(src).b200_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "b200_cast_f32_to_bf16")
+    _count(1)
     return dst
 
 
 def scale_f32_(x, scale_dev=None, scale_host=1.0):
     _req(x.dtype == F32 and x.is_contiguous(), "scale_f32: contiguous fp32 expected")
     check(_L(x).b200_scale_f32(ptr(x), x.numel(), ptr(scale_dev), float(scale_host), stream_ptr()), "b200_scale_f32")
+    _count(1)
     return x

@@ -294,6 +294,15 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         p = f"gpt_neox.layers.{i}"
         return self.flat.range_of([n for n in self.flat.names if n.startswith(p + ".")])
 
+    def _head_range(self) -> tuple[int, int]:
+        return self.flat.range_of(["gpt_neox.final_layer_norm.weight", "gpt_neox.final_layer_norm.bias", "embed_out.weight"])
+
+    def comm_buckets(self) -> list[tuple[int, int]]:
+        """Flat-grad element ranges in the order backward completes them (head, layers L-1..0, input embedding); these
+        are the DDP / ZeRO-1 communication buckets `grad_ready_hook` is fired with."""
+        return [self._head_range()] + [self._layer_range(i) for i in reversed(range(self.L))] + \
+               [self.flat.range_of(["gpt_neox.embed_in.weight"])]
+
     # ------------------------------------------------------------------ whole-model forward / backward
     def _forward_hidden(self, ids: torch.Tensor, keep: bool):
         B, S = ids.shape

@@ -55,33 +55,52 @@ class B200Adam(torch.optim.Optimizer):
     def _build(self) -> None:
         f: FlatParams = self._flat
         dev = f.master.device
-        lo, hi = self._shard if self._shard is not None else (0, f.numel)
-        starts, lens, grps = [], [], []
+        ranges = self._ranges()
+        # state offset of each owned range: ranges are packed back to back in the (sharded) moment buffers
+        state_off, acc = [], 0
+        for lo, hi in ranges:
+            state_off.append(acc)
+            acc += hi - lo
+        starts, lens, grps, soffs = [], [], [], []
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 _, off, n = p._b200_flat
-                a, b = max(off, lo), min(off + n, hi)
-                c = a
-                while c < b:
-                    ln = min(CHUNK, b - c)
-                    starts.append(c), lens.append(ln), grps.append(gi)
-                    c += ln
+                for (lo, hi), so in zip(ranges, state_off):
+                    a, b = max(off, lo), min(off + n, hi)
+                    c = a
+                    while c < b:
+                        ln = min(CHUNK, b - c)
+                        starts.append(c), lens.append(ln), grps.append(gi), soffs.append(so + (c - lo))
+                        c += ln
         self._chunk_start = torch.tensor(starts, dtype=torch.int64, device=dev)
         self._chunk_len = torch.tensor(lens, dtype=torch.int32, device=dev)
         self._chunk_group = torch.tensor(grps, dtype=torch.int32, device=dev)
-        self._state_base = lo
-        if self._m is None or self._m.numel() != hi - lo or self._m.device != dev:
+        self._chunk_state = torch.tensor(soffs, dtype=torch.int64, device=dev)
+        self._state_base = 0
+        if self._m is None or self._m.numel() != acc or self._m.device != dev:
             m_old, v_old = self._m, self._v
-            self._m = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
-            self._v = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
-            if m_old is not None and m_old.numel() == hi - lo:
+            self._m = torch.zeros(acc, dtype=torch.float32, device=dev)
+            self._v = torch.zeros(acc, dtype=torch.float32, device=dev)
+            if m_old is not None and m_old.numel() == acc:
                 self._m.copy_(m_old), self._v.copy_(v_old)
-        self._built_for = (dev, f.master.data_ptr(), lo, hi)
+        self._built_for = (dev, f.master.data_ptr(), tuple(ranges))
+
+    def _ranges(self) -> list[tuple[int, int]]:
+        if self._shard is None:
+            return [(0, self._flat.numel)]
+        if isinstance(self._shard, tuple) and len(self._shard) == 2 and isinstance(self._shard[0], int):
+            return [self._shard]
+        return [tuple(r) for r in self._shard]
+
+    def set_shard(self, ranges) -> None:
+        """ZeRO-1: restrict the update (and the moment buffers) to the flat-buffer element ranges this rank owns."""
+        self._shard = ranges
+        self._built_for = None
+        self._m = self._v = None
 
     def _ensure_built(self) -> None:
         f = self._flat
-        lo, hi = self._shard if self._shard is not None else (0, f.numel)
-        if self._built_for != (f.master.device, f.master.data_ptr(), lo, hi):
+        if self._built_for != (f.master.device, f.master.data_ptr(), tuple(self._ranges())):
             self._build()
 
     # ------------------------------------------------------------------ torch.optim API
@@ -107,7 +126,8 @@ class B200Adam(torch.optim.Optimizer):
         f.pending_grad_scale = None
         f.sync_shadow()  # no-op unless the master was edited through torch since the last step
         K.adam_step(f.master, f.grad, self._m, self._v, f.shadow, self._state_base, self._chunk_start, self._chunk_len,
-                    self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step)
+                    self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step,
+                    chunk_state=self._chunk_state)
         return loss
 
     def zero_grad(self, set_to_none: bool = False) -> None:
