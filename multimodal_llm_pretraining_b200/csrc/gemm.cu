@@ -3,13 +3,16 @@
 // Replaces nn.Linear forward / dgrad / wgrad (cuBLAS in the reference stack; HF:modeling_gpt_neox.py:41-42,200-201,464).
 //
 // Persistent: one CTA per SM walks output tiles (grouped raster so weight tiles stay hot in the 126 MB L2).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  Three mbarrier pipelines: smem full/empty per stage,
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue in two groups of four (TMEM lane quarter = warp_idx % 4; groups alternate 64-column slabs).
+// bf16 outputs are staged as 128x64 swizzled slabs in smem and written with TMA stores (full cache lines).  Three mbarrier pipelines: smem full/empty per stage,
 // TMEM full/empty per accumulator buffer — the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Operand majorness is handled in hardware through the smem descriptors (no transposes in HBM):
 //   K-major  X[R, K]: TMA box {64 k, R rows}, rows of 128 B, SBO = 1024.
 //   MN-major X[K, R]: TMA boxes {64 r, 64 k} per 64-wide slice of R, LBO = 8192 (slice pitch), SBO = 1024.
+#include <stdlib.h>
+
 #include "api.h"
 #include "common.cuh"
 
@@ -17,7 +20,7 @@ namespace b200 {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
 
 struct GemmParams {
     int M, N, K;
@@ -33,6 +36,8 @@ struct GemmParams {
     __nv_bfloat16* aux_out;
     const __nv_bfloat16* dgelu_in;
     int tiles_m, tiles_n;
+    int tma_store;  // bf16 output without accumulate: stage 128x64 slabs in smem and TMA-store them (full-line writes)
+    int debug;  // B200_GEMM_DEBUG (perf triage only): bit0 = skip epilogue math+stores, bit1 = skip TMEM loads as well
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -47,9 +52,26 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     tn = r / gm;
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], int row, int col0, float alpha) {
-    if (row >= p.M) return;
+template <int BN, int STAGES>
+constexpr size_t gemm_smem_bytes() {
+    // ring + barriers (256) + bias [2][BN] fp32 + two 16 KB output slabs + alignment slack; the 227 KB per-CTA limit
+    // (232448 B) leaves 256 B of slack less than a full 1 KB for BN=256 — the kernel traps if the base is that unlucky.
+    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 256 + 2 * BN * 4 + 32768;
+    return need + 1024 <= 232448 ? need + 1024 : 232448;
+}
+
+// `side` = the 32-column slice of the residual / dgelu_in row, prefetched one chunk ahead so that its global-load latency
+// overlaps the previous chunk's math; `sbias` = this tile's bias staged in shared memory (one coalesced load per tile).
+// With p.tma_store the bf16 results go to the 128-row x 64-column SWIZZLE_128B staging slab in shared memory
+// (`stage_main`, this chunk being half `half` of the slab, `r` = row inside the tile) instead of global.
+// EPI (compile time, keeps the instruction footprint of the hot loop small — a fully generic, fully unrolled epilogue
+// was 350 KB of SASS and instruction-fetch bound): 0 = bias/residual/alpha/accumulate, 1 = + exact-erf GELU (+ aux
+// pre-activation output), 2 = + multiply by gelu'(dgelu_in).
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], const uint4 (&side)[4],
+                                               const float* sbias, int row, int col0, float alpha, uint8_t* stage_main,
+                                               int half, int r) {
+    if (!p.tma_store && row >= p.M) return;
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
@@ -59,21 +81,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         if (col >= p.N) break;  // N % 8 == 0
         float* x = &f[g8 * 8];
         if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias + g8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias + g8 * 8 + 4);
             x[0] += b0.x, x[1] += b0.y, x[2] += b0.z, x[3] += b0.w;
             x[4] += b1.x, x[5] += b1.y, x[6] += b1.z, x[7] += b1.w;
         }
-        if (p.aux_out) {
-            st_v4(p.aux_out + static_cast<size_t>(row) * p.ldc + col,
-                  make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7])));
+        if (EPI == 1 && p.aux_out) {
+            const uint4 av = make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7]));
+            if (row < p.M) st_v4(p.aux_out + static_cast<size_t>(row) * p.ldc + col, av);
         }
-        if (p.gelu) {
+        if (EPI == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
         }
-        if (p.dgelu_in) {
-            const uint4 hv = ld_nc_v4(p.dgelu_in + static_cast<size_t>(row) * p.ldr + col);
+        if (EPI == 2) {
+            const uint4 hv = side[g8];
             const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -83,7 +105,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             }
         }
         if (p.residual) {
-            const uint4 rv = ld_nc_v4(p.residual + static_cast<size_t>(row) * p.ldr + col);
+            const uint4 rv = side[g8];
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -92,7 +114,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 x[2 * j + 1] += r.y;
             }
         }
-        if (p.c_fp32) {
+        if (p.tma_store) {
+            *reinterpret_cast<uint4*>(stage_main + sw128_offset(r, half * 4 + g8)) =
+                make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7]));
+        } else if (p.c_fp32) {
             float* c = static_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col;
             if (p.accumulate) {
                 const float4 c0 = *reinterpret_cast<const float4*>(c);
@@ -119,9 +144,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
     constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
     constexpr uint32_t SLICE_BYTES = 64 * GEMM_BK * 2;   // one 64-wide MN slice of an MN-major operand (8 KB)
@@ -132,12 +158,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+    constexpr uint32_t RING_BYTES = STAGES * (A_BYTES + B_BYTES);
+    uint8_t* sstage = smem + RING_BYTES;  // 2 x 16 KB output slabs (1024-aligned: the ring is a multiple of 16 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + 32768);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + 32768 + 256);  // [2][BN]
+    static_assert(RING_BYTES % 1024 == 0, "staging slabs must be 1024B aligned");
+    if (threadIdx.x == 0 && (smem + RING_BYTES + 32768 + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes<BN, STAGES>())) {
+        printf("b200pt gemm: dynamic smem base misaligned beyond slack\n");
+        __trap();
+    }
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -153,7 +187,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&tempty[s], 8);
         }
         fence_barrier_init();
     }
@@ -231,9 +265,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++as == 2) as = 0, aph ^= 1;
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+        // ------------------------------------------------------------------ epilogue (warps 2..9, two groups of four)
+        // Group g (warps 2+4g .. 5+4g) owns the 64-column slabs with index = g (mod 2); inside a group warp w reads TMEM
+        // lanes [32*(w%4), +32) (hardware restriction) = output rows. Two warps per SM sub-partition hide the TMEM /
+        // global-load / erf latencies of each other.
+        const int quarter = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const int et_all = threadIdx.x - 64;  // 0..255 over both groups
+        const int et = et_all & 127;          // 0..127 inside the group
+        const int bar_id = 1 + grp;
         const float alpha = p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f;
+        const __nv_bfloat16* side_ptr = p.residual ? p.residual : p.dgelu_in;
+        constexpr int NC = BN / 32;
+        uint8_t* st_main = sstage + grp * 16384;
         int as = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -241,22 +285,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
             const int row = tm * GEMM_BM + quarter * 32 + lane;
             const int n0 = tn * BN;
+            float* sb = sbias + as * BN;
+            if (p.bias) {
+                // buffer `as` was last read two tiles ago; every epilogue warp has passed the barrier of the tile in
+                // between, so it is free. One coalesced load per tile replaces 32 dependent L1 round trips per thread.
+                for (int i = et_all; i < BN; i += 256) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+            }
+            auto load_side = [&](int c, uint4 (&r)[4]) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int col = n0 + c * 32 + g8 * 8;
+                    r[g8] = (side_ptr != nullptr && row < p.M && col < p.N)
+                                ? ld_nc_v4(side_ptr + static_cast<size_t>(row) * p.ldr + col)
+                                : make_uint4(0, 0, 0, 0);
+                }
+            };
+            const int rem = p.N - n0;
+            const int nc_valid = rem >= BN ? NC : (rem + 31) / 32;  // chunks that hold at least one valid column
+            const int r_in_tile = quarter * 32 + lane;
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (n0 + c * 32 >= p.N) break;  // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32(t_addr + c * 32, v);
+            for (int c0 = 2 * grp; c0 < nc_valid; c0 += 4) {  // rolled: one slab (two chunk bodies) of code
+                const bool two = c0 + 1 < nc_valid;
+                uint32_t v0[32], v1[32];
+                uint4 side0[4], side1[4];
+                tmem_ld_32x32(t_addr + c0 * 32, v0);
+                if (two) tmem_ld_32x32(t_addr + (c0 + 1) * 32, v1);
+                load_side(c0, side0);
+                if (two) load_side(c0 + 1, side1);
+                if (p.tma_store) {
+                    // this group's slab buffer must have been drained by the TMA store that last read it
+                    if (et == 0) tma_store_wait_read<0>();
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
                 tmem_ld_wait();
-                epilogue_chunk<BN>(p, v, row, n0 + c * 32, alpha);
+                if (p.debug & 1) continue;
+                epilogue_chunk<EPI>(p, v0, side0, sb + c0 * 32, row, n0 + c0 * 32, alpha, st_main, 0, r_in_tile);
+                if (two) epilogue_chunk<EPI>(p, v1, side1, sb + (c0 + 1) * 32, row, n0 + (c0 + 1) * 32, alpha, st_main, 1, r_in_tile);
+                if (p.tma_store) {
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (et == 0) {
+                        tma_store_2d(&tmC, st_main, n0 + (c0 >> 1) * 64, tm * GEMM_BM);
+                        tma_store_commit();
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
             if (++as == 2) as = 0, aph ^= 1;
         }
+        if (p.tma_store && et == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores reading it
     }
 
     tc_fence_before();
@@ -312,14 +395,11 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
     return 0;
 }
 
-template <int BN, int STAGES>
-constexpr size_t gemm_smem_bytes() {
-    return static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 256 + 1024;
-}
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN>;
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                       const GemmParams& p, cudaStream_t st) {
+    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI>;
     constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
@@ -329,7 +409,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int tiles = p.tiles_m * p.tiles_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, p);
+    kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmAux, p);
     return check_launch("gemm_bf16");
 }
 
@@ -345,10 +425,23 @@ static int dispatch_major(const b200_gemm_args* a, GemmParams& p, cudaStream_t s
     if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, GEMM_BK, BN);
     else          rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, GEMM_BK);
     if (rc) return rc;
-    if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false>(tmA, tmB, p, st);
-    if (!a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, false, true>(tmA, tmB, p, st);
-    if (a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, true, true>(tmA, tmB, p, st);
-    return launch_gemm<BN, STAGES, true, false>(tmA, tmB, p, st);
+    CUtensorMap tmC = tmA, tmAux = tmA;  // placeholders when the TMA-store path is off
+    if (p.tma_store) {
+        if ((rc = make_tmap_bf16_2d(&tmC, a->C, a->N, a->M, a->ldc, 64, GEMM_BM))) return rc;
+        if (a->aux_out && (rc = make_tmap_bf16_2d(&tmAux, a->aux_out, a->N, a->M, a->ldc, 64, GEMM_BM))) return rc;
+    }
+    if (a->gelu) {
+        if (a->a_mn || a->b_mn) return fail(-1, "gemm: the GELU epilogue is built for the forward layout (a_mn=0, b_mn=0) only");
+        return launch_gemm<BN, STAGES, false, false, 1>(tmA, tmB, tmC, tmAux, p, st);
+    }
+    if (a->dgelu_in) {
+        if (a->a_mn || !a->b_mn) return fail(-1, "gemm: the dGELU epilogue is built for the dgrad layout (a_mn=0, b_mn=1) only");
+        return launch_gemm<BN, STAGES, false, true, 2>(tmA, tmB, tmC, tmAux, p, st);
+    }
+    if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false, 0>(tmA, tmB, tmC, tmAux, p, st);
+    if (!a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, false, true, 0>(tmA, tmB, tmC, tmAux, p, st);
+    if (a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, true, true, 0>(tmA, tmB, tmC, tmAux, p, st);
+    return launch_gemm<BN, STAGES, true, false, 0>(tmA, tmB, tmC, tmAux, p, st);
 }
 
 }  // namespace b200
@@ -362,7 +455,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     B200_REQUIRE(a->ldc % 8 == 0 && aligned16(a->C), "gemm: C must be 16B aligned with ldc %% 8 == 0");
     B200_REQUIRE(!a->residual || (a->ldr % 8 == 0 && aligned16(a->residual)), "gemm: residual must be 16B aligned with ldr %% 8 == 0");
     B200_REQUIRE(!a->dgelu_in || (a->ldr % 8 == 0 && aligned16(a->dgelu_in)), "gemm: dgelu_in must be 16B aligned with ldr %% 8 == 0");
-    B200_REQUIRE(!(a->residual && a->dgelu_in) || true, "gemm: ok");
+    B200_REQUIRE(!(a->residual && a->dgelu_in), "gemm: residual and dgelu_in are mutually exclusive");
     B200_REQUIRE(!a->bias || aligned16(a->bias), "gemm: bias must be 16B aligned");
     B200_REQUIRE(!a->aux_out || aligned16(a->aux_out), "gemm: aux_out must be 16B aligned");
     GemmParams p;
@@ -375,6 +468,10 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     p.alpha_dev = a->alpha_dev;
     p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
     p.dgelu_in = static_cast<const __nv_bfloat16*>(a->dgelu_in);
+    static const int dbg = getenv("B200_GEMM_DEBUG") ? atoi(getenv("B200_GEMM_DEBUG")) : 0;
+    p.debug = dbg;
+    p.tma_store = (!a->c_fp32 && !a->accumulate && !(dbg & 64)) ? 1 : 0;
+    B200_REQUIRE(!a->aux_out || a->gelu, "gemm: aux_out is the pre-GELU output and needs gelu=1");
     cudaStream_t st = as_stream(stream);
     // 128 x 256 tiles when N is wide enough to fill them; 128 x 128 otherwise
     if (a->N > 128) return dispatch_major<256, 4>(a, p, st);

@@ -193,7 +193,8 @@ def test_gemm_epilogues(dev):
     h = torch.randn(M, N, generator=g).to(dev).to(BF16)
     hf = h.float().requires_grad_(True)
     torch.nn.functional.gelu(hf).backward(base)
-    check(K.gemm(A, W, dgelu_in=h), hf.grad, 5e-3, "fused dgelu")
+    Wt = W.t().contiguous()  # dgrad layout: B stored [K, N]
+    check(K.gemm(A, Wt, b_mn=True, dgelu_in=h), hf.grad, 5e-3, "fused dgelu")
     acc = torch.randn(M, N, generator=g).to(dev)
     want = acc + base
     K.gemm(A, W, out=acc, accumulate=True)
