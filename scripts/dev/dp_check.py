@@ -1,0 +1,77 @@
+"""torchrun --nproc-per-node W scripts/dev/dp_check.py : DDP and ZeRO-1 over NCCL must give the same parameters as a
+single-process run that accumulates all ranks' micro-batches (gradient mean), within fp32/bf16 tolerance."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+from multimodal_llm_pretraining_b200.engine import TrainEngine
+from multimodal_llm_pretraining_b200.modeling_gpt_neox import B200GPTNeoXForCausalLM
+from multimodal_llm_pretraining_b200.models.configs import as_namespace, pythia_config_dict
+from multimodal_llm_pretraining_b200.optim import B200Adam
+
+
+def build(cfg, dev, seed=0):
+    m = B200GPTNeoXForCausalLM(as_namespace(cfg))
+    m.reset_parameters(torch.Generator().manual_seed(seed))
+    return m.to(dev).train()
+
+
+def main():
+    rank, world, lr_ = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr_)
+    dev = torch.device("cuda", lr_)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(pythia_config_dict("pythia-70m"), num_hidden_layers=3, vocab_size=2048)
+    steps, ga = 3, 2
+    g = torch.Generator().manual_seed(5)
+    data = torch.randint(0, 2048, (steps, ga, world, 4, 257), generator=g)  # [step, micro, rank, mbs, S]
+
+    # reference: one process, all ranks' batches, ga*world accumulation
+    ref = build(cfg, dev)
+    opt = B200Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.95))
+    eng = TrainEngine(ref, opt, None, max_grad_norm=1.0, gradient_accumulation_steps=ga * world, strategy="none")
+    for s in range(steps):
+        for m in range(ga):
+            for r in range(world):
+                ids = data[s, m, r].to(dev)
+                eng.manual_training_step({"input_ids": ids, "labels": ids})
+        eng.manual_optimization_step()
+    ref_master = ref.flat.master.clone()
+
+    ok = True
+    for strategy in ("ddp", "zero1"):
+        model = build(cfg, dev)
+        opt = B200Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.95))
+        eng = TrainEngine(model, opt, None, max_grad_norm=1.0, gradient_accumulation_steps=ga, strategy=strategy)
+        for s in range(steps):
+            for m in range(ga):
+                ids = data[s, m, rank].to(dev)
+                eng.manual_training_step({"input_ids": ids, "labels": ids})
+            eng.manual_optimization_step()
+        torch.cuda.synchronize()
+        upd_ref = ref_master - build(cfg, dev).flat.master
+        upd = model.flat.master - build(cfg, dev).flat.master
+        err = ((upd - upd_ref).norm() / upd_ref.norm()).item()
+        shadow_ok = torch.equal(model.flat.shadow, model.flat.master.to(torch.bfloat16))
+        # all ranks must hold identical parameters
+        chk = model.flat.master.double().sum().reshape(1)
+        lst = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(lst, chk)
+        same = all(torch.equal(lst[0], x) for x in lst)
+        if strategy == "zero1":
+            assert opt._m.numel() * world <= model.flat.numel, "moments must be sharded"
+        good = err < 5e-2 and shadow_ok and same
+        ok = ok and good
+        if rank == 0:
+            print(f"{strategy}: update rel err vs single-process {err:.3e}, shadow in sync {shadow_ok}, ranks identical {same} -> {'OK' if good else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU tests of the reference-surface mirror: model registry, hyper-parameters, TrainingClass -> HF args dict (checked
+against the one golden artefact the reference publishes: README.md:77-124), data sharding (bit exact), FLOP metric."""
+import json
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from multimodal_llm_pretraining_b200.benchmarking.data import DummyTextModelingDataset, ShardedBatchIterator, shard_rows  # noqa: E402
+from multimodal_llm_pretraining_b200.config import TrainingConfig  # noqa: E402
+from multimodal_llm_pretraining_b200.models import get_model_class  # noqa: E402
+from multimodal_llm_pretraining_b200.models import configs as C  # noqa: E402
+
+
+def test_param_counts_match_published():
+    for name, n in C.PYTHIA_PARAM_COUNTS.items():
+        assert C.neox_param_count(C.pythia_config_dict(name)) == n, name
+
+
+def test_flat_module_param_count_and_hf_keys():
+    from multimodal_llm_pretraining_b200.modeling_gpt_neox import B200GPTNeoXForCausalLM
+
+    cfg = C.pythia_config_dict("pythia-70m")
+    m = B200GPTNeoXForCausalLM(C.as_namespace(cfg))
+    assert sum(p.numel() for p in m.parameters()) == C.PYTHIA_PARAM_COUNTS["pythia-70m"]
+    tr = pytest.importorskip("transformers")
+    with torch.device("meta"):
+        hf = tr.GPTNeoXForCausalLM(tr.GPTNeoXConfig(**cfg))
+    hf_keys = sorted(k for k in hf.state_dict() if "inv_freq" not in k)
+    assert sorted(m.state_dict()) == hf_keys
+    for k, v in hf.state_dict().items():
+        if "inv_freq" not in k:
+            assert m.state_dict()[k].shape == v.shape, k
+    # init statistics follow HF (N(0, 0.02), LN (1,0), bias 0)
+    w = m.state_dict()["gpt_neox.layers.0.mlp.dense_h_to_4h.weight"]
+    assert abs(w.std().item() - 0.02) < 2e-3 and abs(w.mean().item()) < 1e-3
+    assert torch.all(m.state_dict()["gpt_neox.layers.0.input_layernorm.weight"] == 1)
+
+
+def test_readme_training_arguments_golden():
+    """scripts/to_training_arguments.py output for pythia-1b / free-lunch / zero_1 / mbs 16 / ga 16 (reference README.md:60-124)."""
+    gold = json.load(open(ROOT / "tests" / "golden" / "readme_training_arguments.json"))
+    cfg = TrainingConfig(num_nodes=1, gpus_per_node=4, gpu_type="a100", model="pythia-1b", free_lunch=True, sharding="zero_1")
+    got = cfg.training_class(micro_batch_size=16, gradient_accumulation_steps=16)._to_huggingface_args_dict()
+    assert json.loads(json.dumps(got)) == gold
+
+
+def test_hyperparameters_follow_reference():
+    p = get_model_class("pythia-1b")
+    assert (p.batch_size, p.training_steps, p.mixed_precision, p.max_grad_norm) == (1024, 143000, "bf16", 1.0)
+    assert p.optimizer_kwargs == {"lr": 3e-4, "betas": (0.9, 0.95), "eps": 1e-8, "weight_decay": 0.01}
+    assert p.scheduler_type.value == "cosine_with_min_lr" and p.scheduler_kwargs == {"num_warmup_steps": 1430, "min_lr_rate": 0.1}
+    assert (p.vocab_size, p.sequence_length) == (50304, 2049)
+    assert get_model_class("pythia-160m").mixed_precision == "fp16" and get_model_class("pythia-160m").optimizer_kwargs["lr"] == 6e-4
+    r = get_model_class("roberta")
+    assert (r.batch_size, r.training_steps, r.max_grad_norm, r.vocab_size, r.sequence_length) == (8192, 500000, 0.0, 50265, 512)
+    with pytest.raises(NotImplementedError):
+        get_model_class("mamba")
+    for sharding in ("zero_2", "fsdp_full_shard"):
+        tc = TrainingConfig(1, 8, "b200", "pythia-1b", sharding=sharding).training_class()
+        assert tc.is_valid() and not tc.runs_on_b200_engine()
+
+
+def test_flop_metric_closed_form():
+    from multimodal_llm_pretraining_b200.benchmarking.flops import count_flops_per_example
+
+    f = count_flops_per_example(get_model_class("pythia-1b"))
+    assert abs(f - 12_817_874_812_992) / f < 1e-7  # FlopCounterMode value quoted in BASELINE.md
+    assert abs(f / 2048 - 6.259e9) / 6.259e9 < 1e-3
+
+
+def test_dummy_dataset_and_sharding_bit_exact():
+    ds = DummyTextModelingDataset(vocab_size=50304, sequence_length=2049, num_samples=64, seed=7)
+    assert ds.input_ids.dtype == torch.int64 and ds.input_ids.shape == (64, 2049)
+    assert torch.equal(ds.input_ids, ds.labels) and ds.labels.data_ptr() != ds.input_ids.data_ptr()
+    item = ds[3]
+    assert set(item) == {"input_ids", "labels"} and int(ds.input_ids.max()) < 50304
+    # every batch of 4 rows is consumed exactly once per epoch, round-robin over ranks
+    W, mbs = 2, 4
+    seen = []
+    for t in range(64 // (W * mbs)):
+        for r in range(W):
+            seen.append(shard_rows(64, mbs, W, r, t))
+    assert torch.equal(torch.cat(seen).sort().values, torch.arange(64))
+    assert torch.equal(shard_rows(64, mbs, W, 1, 0), torch.arange(4, 8))
+    assert torch.equal(shard_rows(64, mbs, W, 0, 1), torch.arange(8, 12))
+    it0 = ShardedBatchIterator(ds, mbs, W, 0, shuffle_seed=0, pin=False)
+    it1 = ShardedBatchIterator(ds, mbs, W, 1, shuffle_seed=0, pin=False)
+    b0, b1 = next(it0), next(it1)
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(b0["input_ids"], ds.input_ids[perm[0:4]]) and torch.equal(b1["input_ids"], ds.input_ids[perm[4:8]])
+    assert torch.equal(b0["labels"], b0["input_ids"])
