@@ -2,7 +2,16 @@
 // accumulators in TMEM (double-buffered, 2 x BN columns) -> tcgen05.ld epilogue warps.
 // Replaces nn.Linear forward / dgrad / wgrad (cuBLAS in the reference stack; HF:modeling_gpt_neox.py:41-42,200-201,464).
 //
-// Persistent: one CTA per SM walks output tiles (grouped raster so weight tiles stay hot in the 126 MB L2).
+// Two tile engines share this file:
+//   CG = 2 (default for M > 128, N > 128): CTA PAIRS (cluster of 2, tcgen05.mma.cta_group::2) compute 256 x 256 output
+//           tiles; each CTA stages its own 128 rows of A and ONE HALF of the B tile, so B is read from shared memory and
+//           fetched from L2 once per pair — 2/3 of the operand bytes per FLOP of the single-CTA engine, which is what
+//           bounds a 128 x 256 x 64 stage (96 B/clk of the 128 B/clk shared-memory port).
+//   CG = 1: one CTA per 128 x BN tile (narrow / short problems).
+// Persistent: one CTA (pair) per SM (TPC) walks output tiles (grouped raster so weight tiles stay hot in the 126 MB L2).
+// Batched mode (CG = 2 only): Z independent problems addressed through per-batch coordinate offsets into the same
+// tensor maps, optional causal reduction range (k >= first row of the tile) — the dK / dV contractions of the
+// attention backward over materialised P / dS tiles (attention.cu).
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..9 = epilogue in two groups of four (TMEM lane quarter = warp_idx % 4; groups alternate 64-column slabs).
 // bf16 outputs are staged as 128x64 swizzled slabs in smem and written with TMA stores (full cache lines).  Three mbarrier pipelines: smem full/empty per stage,
@@ -37,6 +46,14 @@ struct GemmParams {
     const __nv_bfloat16* dgelu_in;
     int tiles_m, tiles_n;
     int tma_store;  // bf16 output without accumulate: stage 128x64 slabs in smem and TMA-store them (full-line writes)
+    // batched mode: problem z = zb * zH + zh adds (zb * x_b + zh * x_h) to the TMA coordinate x of each operand
+    int Z, zH;
+    int a_k_b, a_k_h, a_m_b, a_m_h;
+    int b_k_b, b_k_h, b_n_b, b_n_h;
+    int c_m_b, c_m_h, c_n_b, c_n_h;
+    int causal_k;  // reduction starts at k = first output row of the tile (rows of A^T below the diagonal are zero)
+    float alpha_host;
+    int split_k;  // fp32-accumulate outputs only: the reduction is cut into split_k ranges, each red.add'ed into C
     int debug;  // B200_GEMM_DEBUG (perf triage only): bit0 = skip epilogue math+stores, bit1 = skip TMEM loads as well
 };
 
@@ -70,7 +87,7 @@ constexpr size_t gemm_smem_bytes() {
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], const uint4 (&side)[4],
                                                const float* sbias, int row, int col0, float alpha, uint8_t* stage_main,
-                                               int half, int r) {
+                                               uint8_t* stage_aux, int half, int r) {
     if (!p.tma_store && row >= p.M) return;
     float f[32];
 #pragma unroll
@@ -88,7 +105,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         }
         if (EPI == 1 && p.aux_out) {
             const uint4 av = make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7]));
-            if (row < p.M) st_v4(p.aux_out + static_cast<size_t>(row) * p.ldc + col, av);
+            if (p.tma_store) st_shared_v4(stage_aux + sw128_offset(r, half * 4 + g8), av);
+            else if (row < p.M) st_v4(p.aux_out + static_cast<size_t>(row) * p.ldc + col, av);
         }
         if (EPI == 1) {
 #pragma unroll
@@ -115,18 +133,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             }
         }
         if (p.tma_store) {
-            *reinterpret_cast<uint4*>(stage_main + sw128_offset(r, half * 4 + g8)) =
-                make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7]));
+            st_shared_v4(stage_main + sw128_offset(r, half * 4 + g8),
+                         make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7])));
         } else if (p.c_fp32) {
             float* c = static_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col;
             if (p.accumulate) {
-                const float4 c0 = *reinterpret_cast<const float4*>(c);
-                const float4 c1 = *reinterpret_cast<const float4*>(c + 4);
-                x[0] += c0.x, x[1] += c0.y, x[2] += c0.z, x[3] += c0.w;
-                x[4] += c1.x, x[5] += c1.y, x[6] += c1.z, x[7] += c1.w;
+                // C += x without reading C: one vector reduction per 16 B, resolved in L2 (also what makes split-K free
+                // of a fix-up pass: every k-range of a tile just adds its partial sum)
+                red_add_v4(c, x[0], x[1], x[2], x[3]);
+                red_add_v4(c + 4, x[4], x[5], x[6], x[7]);
+            } else {
+                *reinterpret_cast<float4*>(c) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(c + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
-            *reinterpret_cast<float4*>(c) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(c + 4) = make_float4(x[4], x[5], x[6], x[7]);
         } else {
             __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col;
             if (p.accumulate) {
@@ -144,38 +163,63 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+template <int CG>
+struct GemmGeom {
+    static constexpr int TILE_M = GEMM_BM * CG;  // output rows per tile (per CTA pair when CG = 2)
+};
+
+// smem per CTA: ring of STAGES x (A 16 KB + B (BN/CG) x 128 B) + two 16 KB output slabs + barriers + bias [2][BN]
+template <int EPI>
+constexpr uint32_t gemm_stage_bytes() {
+    return EPI == 1 ? 65536u : 32768u;  // per epilogue group: one 16 KB output slab (+ one for the pre-GELU aux output)
+}
+template <int BN, int STAGES, int CG, int EPI>
+constexpr size_t gemm_smem_bytes_cg() {
+    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<EPI>();
+    return need + 1024 <= 232448 ? need + 1024 : 232448;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+    constexpr int BNH = BN / CG;                          // B rows staged by this CTA
+    constexpr int TILE_M = GEMM_BM * CG;
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-    constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+    constexpr uint32_t B_BYTES = BNH * GEMM_BK * 2;
     constexpr uint32_t SLICE_BYTES = 64 * GEMM_BK * 2;   // one 64-wide MN slice of an MN-major operand (8 KB)
     constexpr uint32_t TMEM_COLS = 2 * BN;
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+    static_assert(CG == 1 || CG == 2, "cta_group");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     constexpr uint32_t RING_BYTES = STAGES * (A_BYTES + B_BYTES);
-    uint8_t* sstage = smem + RING_BYTES;  // 2 x 16 KB output slabs (1024-aligned: the ring is a multiple of 16 KB)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + 32768);
+    constexpr uint32_t STG = gemm_stage_bytes<EPI>();
+    uint8_t* sstage = smem + RING_BYTES;  // output slabs (1024-aligned: the ring is a multiple of 16 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STG);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + 32768 + 256);  // [2][BN]
+    float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + STG + 256);  // [2][BN]
     static_assert(RING_BYTES % 1024 == 0, "staging slabs must be 1024B aligned");
-    if (threadIdx.x == 0 && (smem + RING_BYTES + 32768 + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes<BN, STAGES>())) {
+    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier block overflow");
+    if (threadIdx.x == 0 && (smem + RING_BYTES + STG + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes_cg<BN, STAGES, CG, EPI>())) {
         printf("b200pt gemm: dynamic smem base misaligned beyond slack\n");
         __trap();
     }
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;  // 0 = leader (issues the MMAs)
+    const int worker = CG == 2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const int n_workers = CG == 2 ? (gridDim.x >> 1) : gridDim.x;
+    const int tiles_per_z = p.tiles_m * p.tiles_n;
+    const int num_tiles = tiles_per_z * p.Z * p.split_k;  // work units: (k-range, problem, tile)
     const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
     if (warp == 0 && lane == 0) {
@@ -187,83 +231,120 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 8);
+            mbar_init(&tempty[s], 8 * CG);  // every epilogue warp of every CTA of the pair
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (CG == 2) {
+            tmem_alloc_pair(tmem_slot, TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile -> (z, tm, tn), first k block; identical in every role
+    auto decode = [&](int unit, int& z, int& tm, int& tn, int& kb0, int& kb1) {
+        const int per_split = tiles_per_z * p.Z;
+        const int ks = unit / per_split;
+        const int tile = unit - ks * per_split;
+        z = tile / tiles_per_z;
+        tile_coords(tile - z * tiles_per_z, p.tiles_m, p.tiles_n, tm, tn);
+        kb0 = p.causal_k ? (tm * TILE_M) / GEMM_BK : 0;
+        kb1 = num_kb;
+        if (p.split_k > 1) {
+            kb0 = static_cast<int>(static_cast<int64_t>(num_kb) * ks / p.split_k);
+            kb1 = static_cast<int>(static_cast<int64_t>(num_kb) * (ks + 1) / p.split_k);
+        }
+    };
+
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        int s = 0;
-        uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            int tm, tn;
-            tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-            const int m0 = tm * GEMM_BM, n0 = tn * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty[s], ph ^ 1);
-                if (lane == 0) {
-                    mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        // ------------------------------------------------------------------ TMA producer (every CTA loads its own half)
+        // ONE thread runs the whole loop: no warp-wide waits, no reconvergence, no election per iteration.
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = worker; tile < num_tiles; tile += n_workers) {
+                int z, tm, tn, kb0, kb1;
+                decode(tile, z, tm, tn, kb0, kb1);
+                const int zb = z / p.zH, zh = z - zb * p.zH;
+                const int m0 = tm * TILE_M + static_cast<int>(rank) * GEMM_BM + zb * p.a_m_b + zh * p.a_m_h;
+                const int n0 = tn * BN + static_cast<int>(rank) * BNH + zb * p.b_n_b + zh * p.b_n_h;
+                const int ak0 = zb * p.a_k_b + zh * p.a_k_h, bk0 = zb * p.b_k_b + zh * p.b_k_h;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[s], CG * (A_BYTES + B_BYTES));
                     uint8_t* a_dst = sA + s * A_BYTES;
                     uint8_t* b_dst = sB + s * B_BYTES;
+                    auto ld = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+                        if (CG == 2) tma_load_2d_pair(dst, m, &full[s], c0, c1);
+                        else tma_load_2d(dst, m, &full[s], c0, c1);
+                    };
                     if (!A_MN) {
-                        tma_load_2d(a_dst, &tmA, &full[s], kb * GEMM_BK, m0);
+                        ld(a_dst, &tmA, ak0 + kb * GEMM_BK, m0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d(a_dst + j * SLICE_BYTES, &tmA, &full[s], m0 + j * 64, kb * GEMM_BK);
+                        for (int j = 0; j < GEMM_BM / 64; ++j) ld(a_dst + j * SLICE_BYTES, &tmA, m0 + j * 64, ak0 + kb * GEMM_BK);
                     }
                     if (!B_MN) {
-                        tma_load_2d(b_dst, &tmB, &full[s], kb * GEMM_BK, n0);
+                        ld(b_dst, &tmB, bk0 + kb * GEMM_BK, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * SLICE_BYTES, &tmB, &full[s], n0 + j * 64, kb * GEMM_BK);
+                        for (int j = 0; j < BNH / 64; ++j) ld(b_dst + j * SLICE_BYTES, &tmB, n0 + j * 64, bk0 + kb * GEMM_BK);
                     }
+                    if (++s == STAGES) s = 0, ph ^= 1;
                 }
-                __syncwarp();
-                if (++s == STAGES) s = 0, ph ^= 1;
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
-        int s = 0;
-        uint32_t ph = 0;
-        int as = 0;
-        uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty[as], aph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full[s], ph);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only, ONE thread)
+        // The loop body must cost fewer issue cycles than the 4 x 128 tensor cycles it feeds: descriptors are advanced
+        // by adding (byte offset >> 4) to precomputed 64-bit templates, and nothing in the loop is warp-collective.
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN, B_MN);
+            const uint64_t adesc0 = A_MN ? umma_desc_sw128(smem_u32(sA), SLICE_BYTES, 1024) : umma_desc_sw128(smem_u32(sA), 16, 1024);
+            const uint64_t bdesc0 = B_MN ? umma_desc_sw128(smem_u32(sB), SLICE_BYTES, 1024) : umma_desc_sw128(smem_u32(sB), 16, 1024);
+            constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int tile = worker; tile < num_tiles; tile += n_workers) {
+                int z, tm, tn, kb0, kb1;
+                decode(tile, z, tm, tn, kb0, kb1);
+                mbar_wait(&tempty[as], aph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t ad = adesc0 + static_cast<uint64_t>((s * A_BYTES) >> 4);
+                    const uint64_t bd = bdesc0 + static_cast<uint64_t>((s * B_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t adesc = A_MN ? umma_desc_sw128(a_addr + k * 2048, SLICE_BYTES, 1024)
-                                                    : umma_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bdesc = B_MN ? umma_desc_sw128(b_addr + k * 2048, SLICE_BYTES, 1024)
-                                                    : umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+                        if (CG == 2) umma_ss_pair(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0) || k != 0);
+                        else umma_ss(d_tmem, ad + k * A_KSTEP, bd + k * B_KSTEP, idesc, (kb > kb0) || k != 0);
                     }
-                    tc_commit(&empty[s]);                       // frees the smem slot when these MMAs retire
-                    if (kb == num_kb - 1) tc_commit(&tfull[as]);  // accumulator complete -> epilogue
+                    if (CG == 2) {
+                        tc_commit_pair(&empty[s], 3);                      // frees the slot in BOTH CTAs
+                        if (kb == kb1 - 1) tc_commit_pair(&tfull[as], 3);  // accumulators complete in both CTAs
+                    } else {
+                        tc_commit(&empty[s]);
+                        if (kb == kb1 - 1) tc_commit(&tfull[as]);
+                    }
+                    if (++s == STAGES) s = 0, ph ^= 1;
                 }
-                __syncwarp();
-                if (++s == STAGES) s = 0, ph ^= 1;
+                if (++as == 2) as = 0, aph ^= 1;
             }
-            if (++as == 2) as = 0, aph ^= 1;
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9, two groups of four)
         // Group g (warps 2+4g .. 5+4g) owns the 64-column slabs with index = g (mod 2); inside a group warp w reads TMEM
@@ -274,17 +355,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int et_all = threadIdx.x - 64;  // 0..255 over both groups
         const int et = et_all & 127;          // 0..127 inside the group
         const int bar_id = 1 + grp;
-        const float alpha = p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f;
+        const float alpha = (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f) * p.alpha_host;
         const __nv_bfloat16* side_ptr = p.residual ? p.residual : p.dgelu_in;
         constexpr int NC = BN / 32;
-        uint8_t* st_main = sstage + grp * 16384;
+        uint8_t* st_main = sstage + grp * (STG / 2);
+        uint8_t* st_aux = st_main + 16384;  // EPI == 1 only
+        const bool has_side = side_ptr != nullptr;
         int as = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            int tm, tn;
-            tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-            const int row = tm * GEMM_BM + quarter * 32 + lane;
+        for (int tile = worker; tile < num_tiles; tile += n_workers) {
+            int z, tm, tn, kb0, kb1;
+            decode(tile, z, tm, tn, kb0, kb1);
+            const int zb = z / p.zH, zh = z - zb * p.zH;
+            const int row0 = tm * TILE_M + static_cast<int>(rank) * GEMM_BM;  // first row of this CTA's 128-row slab
+            const int row = row0 + quarter * 32 + lane;
             const int n0 = tn * BN;
+            const int c_m0 = row0 + zb * p.c_m_b + zh * p.c_m_h, c_n0 = n0 + zb * p.c_n_b + zh * p.c_n_h;
             float* sb = sbias + as * BN;
             if (p.bias) {
                 // buffer `as` was last read two tiles ago; every epilogue warp has passed the barrier of the tile in
@@ -296,7 +382,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8) {
                     const int col = n0 + c * 32 + g8 * 8;
-                    r[g8] = (side_ptr != nullptr && row < p.M && col < p.N)
+                    r[g8] = (has_side && row < p.M && col < p.N)
                                 ? ld_nc_v4(side_ptr + static_cast<size_t>(row) * p.ldr + col)
                                 : make_uint4(0, 0, 0, 0);
                 }
@@ -304,6 +390,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int rem = p.N - n0;
             const int nc_valid = rem >= BN ? NC : (rem + 31) / 32;  // chunks that hold at least one valid column
             const int r_in_tile = quarter * 32 + lane;
+            // The residual / dgelu_in slices do not depend on the accumulator: fetch the first slab's before waiting for
+            // the MMAs and every later slab's one iteration ahead, so their HBM latency never sits on the critical path.
+            uint4 side0[4], side1[4];
+            if (has_side) {
+                load_side(2 * grp, side0);
+                load_side(2 * grp + 1, side1);
+            }
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
@@ -311,11 +404,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int c0 = 2 * grp; c0 < nc_valid; c0 += 4) {  // rolled: one slab (two chunk bodies) of code
                 const bool two = c0 + 1 < nc_valid;
                 uint32_t v0[32], v1[32];
-                uint4 side0[4], side1[4];
+                uint4 nside0[4], nside1[4];
                 tmem_ld_32x32(t_addr + c0 * 32, v0);
                 if (two) tmem_ld_32x32(t_addr + (c0 + 1) * 32, v1);
-                load_side(c0, side0);
-                if (two) load_side(c0 + 1, side1);
+                if (has_side && c0 + 4 < nc_valid) {
+                    load_side(c0 + 4, nside0);
+                    load_side(c0 + 5, nside1);
+                }
                 if (p.tma_store) {
                     // this group's slab buffer must have been drained by the TMA store that last read it
                     if (et == 0) tma_store_wait_read<0>();
@@ -323,30 +418,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 tmem_ld_wait();
                 if (p.debug & 1) continue;
-                epilogue_chunk<EPI>(p, v0, side0, sb + c0 * 32, row, n0 + c0 * 32, alpha, st_main, 0, r_in_tile);
-                if (two) epilogue_chunk<EPI>(p, v1, side1, sb + (c0 + 1) * 32, row, n0 + (c0 + 1) * 32, alpha, st_main, 1, r_in_tile);
+                epilogue_chunk<EPI>(p, v0, side0, sb + c0 * 32, row, n0 + c0 * 32, alpha, st_main, st_aux, 0, r_in_tile);
+                if (two) epilogue_chunk<EPI>(p, v1, side1, sb + (c0 + 1) * 32, row, n0 + (c0 + 1) * 32, alpha, st_main, st_aux, 1, r_in_tile);
                 if (p.tma_store) {
                     fence_proxy_async_smem();
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (et == 0) {
-                        tma_store_2d(&tmC, st_main, n0 + (c0 >> 1) * 64, tm * GEMM_BM);
+                        tma_store_2d(&tmC, st_main, c_n0 + (c0 >> 1) * 64, c_m0);
+                        if (EPI == 1 && p.aux_out) tma_store_2d(&tmAux, st_aux, c_n0 + (c0 >> 1) * 64, c_m0);
                         tma_store_commit();
                     }
+                }
+                if (has_side) {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) side0[g8] = nside0[g8], side1[g8] = nside1[g8];
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tempty[as], 0);  // the leader's barrier gates the next MMA into this buffer
+                else mbar_arrive(&tempty[as]);
+            }
             if (++as == 2) as = 0, aph ^= 1;
         }
         if (p.tma_store && et == 0) tma_store_wait_all<0>();  // smem must outlive the bulk stores reading it
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();  // nobody leaves while the peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -396,52 +500,119 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
 }
 
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+// deepest ring <= STAGES that still fits next to the GELU variant's second output slab
+template <int BN, int STAGES, int CG>
+constexpr int gelu_stages() {
+    int st = STAGES;
+    while (static_cast<size_t>(st) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<1>() + 1024 > 232448) --st;
+    return st;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI>;
-    constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, CG>;
+    constexpr size_t smem = gemm_smem_bytes_cg<BN, STAGES, CG, EPI>();
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return fail(-2, "gemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
         configured = true;
     }
-    const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, tmC, tmAux, p);
+    const int tiles = p.tiles_m * p.tiles_n * p.Z * p.split_k;
+    const int workers_max = num_sms() / CG;  // CTA pairs need both SMs of a TPC
+    const int workers = tiles < workers_max ? tiles : workers_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CG, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmAux, p);
+    if (e != cudaSuccess) return fail(-2, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");
 }
 
-template <int BN, int STAGES>
-static int dispatch_major(const b200_gemm_args* a, GemmParams& p, cudaStream_t st) {
-    p.tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+template <int BN, int STAGES, int CG>
+static int dispatch_major(const b200_gemm_args* a, GemmParams& p, cudaStream_t st, const CUtensorMap* tmC_override = nullptr,
+                          uint64_t a_rows_total = 0, uint64_t b_rows_total = 0) {
+    constexpr int TILE_M = GEMM_BM * CG;
+    constexpr int BNH = BN / CG;
+    p.tiles_m = (p.M + TILE_M - 1) / TILE_M;
     p.tiles_n = (p.N + BN - 1) / BN;
     CUtensorMap tmA, tmB;
     int rc;
-    if (!a->a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, GEMM_BK, GEMM_BM);
-    else          rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, 64, GEMM_BK);
+    // plain problem: the maps are clipped at the logical extents so that edge tiles are zero-filled; batched problems
+    // address the whole buffers (their per-problem offsets are added to the coordinates in the kernel)
+    const bool batched = p.Z > 1 || a_rows_total || b_rows_total;
+    const uint64_t a_in = batched ? static_cast<uint64_t>(a->lda) : static_cast<uint64_t>(a->a_mn ? a->M : a->K);
+    const uint64_t a_out = batched ? a_rows_total : static_cast<uint64_t>(a->a_mn ? a->K : a->M);
+    const uint64_t b_in = batched ? static_cast<uint64_t>(a->ldb) : static_cast<uint64_t>(a->b_mn ? a->N : a->K);
+    const uint64_t b_out = batched ? b_rows_total : static_cast<uint64_t>(a->b_mn ? a->K : a->N);
+    if (!a->a_mn) rc = make_tmap_bf16_2d(&tmA, a->A, a_in, a_out, a->lda, GEMM_BK, GEMM_BM);
+    else          rc = make_tmap_bf16_2d(&tmA, a->A, a_in, a_out, a->lda, 64, GEMM_BK);
     if (rc) return rc;
-    if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, GEMM_BK, BN);
-    else          rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, GEMM_BK);
+    if (!a->b_mn) rc = make_tmap_bf16_2d(&tmB, a->B, b_in, b_out, a->ldb, GEMM_BK, BNH);
+    else          rc = make_tmap_bf16_2d(&tmB, a->B, b_in, b_out, a->ldb, 64, GEMM_BK);
     if (rc) return rc;
     CUtensorMap tmC = tmA, tmAux = tmA;  // placeholders when the TMA-store path is off
     if (p.tma_store) {
-        if ((rc = make_tmap_bf16_2d(&tmC, a->C, a->N, a->M, a->ldc, 64, GEMM_BM))) return rc;
+        if (tmC_override) tmC = *tmC_override;
+        else if ((rc = make_tmap_bf16_2d(&tmC, a->C, a->N, a->M, a->ldc, 64, GEMM_BM))) return rc;
         if (a->aux_out && (rc = make_tmap_bf16_2d(&tmAux, a->aux_out, a->N, a->M, a->ldc, 64, GEMM_BM))) return rc;
     }
     if (a->gelu) {
         if (a->a_mn || a->b_mn) return fail(-1, "gemm: the GELU epilogue is built for the forward layout (a_mn=0, b_mn=0) only");
-        return launch_gemm<BN, STAGES, false, false, 1>(tmA, tmB, tmC, tmAux, p, st);
+        return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, false, 1, CG>(tmA, tmB, tmC, tmAux, p, st);
     }
     if (a->dgelu_in) {
         if (a->a_mn || !a->b_mn) return fail(-1, "gemm: the dGELU epilogue is built for the dgrad layout (a_mn=0, b_mn=1) only");
-        return launch_gemm<BN, STAGES, false, true, 2>(tmA, tmB, tmC, tmAux, p, st);
+        return launch_gemm<BN, STAGES, false, true, 2, CG>(tmA, tmB, tmC, tmAux, p, st);
     }
-    if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false, 0>(tmA, tmB, tmC, tmAux, p, st);
-    if (!a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, false, true, 0>(tmA, tmB, tmC, tmAux, p, st);
-    if (a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, true, true, 0>(tmA, tmB, tmC, tmAux, p, st);
-    return launch_gemm<BN, STAGES, true, false, 0>(tmA, tmB, tmC, tmAux, p, st);
+    if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
+    if (!a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, false, true, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
+    if (a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, true, true, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
+    return launch_gemm<BN, STAGES, true, false, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
+}
+
+static void fill_params(const b200_gemm_args* a, GemmParams& p) {
+    p = GemmParams{};
+    p.M = a->M, p.N = a->N, p.K = a->K;
+    p.C = a->C, p.ldc = a->ldc, p.c_fp32 = a->c_fp32, p.accumulate = a->accumulate;
+    p.bias = a->bias;
+    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.ldr = a->ldr;
+    p.gelu = a->gelu;
+    p.alpha_dev = a->alpha_dev;
+    p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
+    p.dgelu_in = static_cast<const __nv_bfloat16*>(a->dgelu_in);
+    p.Z = 1, p.zH = 1;
+    p.alpha_host = 1.0f;
+    p.split_k = 1;
+}
+
+// dOut[z] = alpha * A[z]^T-or-not x B[z] over Z = nb * nh problems sharing the tensor maps (see GemmParams); bf16 TMA-stored
+// output only. Used by the attention backward (attention.cu).
+int gemm_batched_pair(const b200_gemm_args* a, int nb, int nh, const int (&offs)[12], int causal_k, float alpha,
+                      uint64_t a_rows_total, uint64_t b_rows_total, const CUtensorMap& tmC, cudaStream_t st) {
+    GemmParams p;
+    fill_params(a, p);
+    p.tma_store = 1;
+    p.Z = nb * nh, p.zH = nh;
+    p.a_k_b = offs[0], p.a_k_h = offs[1], p.a_m_b = offs[2], p.a_m_h = offs[3];
+    p.b_k_b = offs[4], p.b_k_h = offs[5], p.b_n_b = offs[6], p.b_n_h = offs[7];
+    p.c_m_b = offs[8], p.c_m_h = offs[9], p.c_n_b = offs[10], p.c_n_h = offs[11];
+    p.causal_k = causal_k;
+    p.alpha_host = alpha;
+    if (a->M % 256 != 0 || a->N % 64 != 0 || a->K % GEMM_BK != 0) return fail(-1, "batched gemm: M %% 256, N %% 64, K %% 64 must be 0 (%d,%d,%d)", a->M, a->N, a->K);
+    if (causal_k && a->K < a->M) return fail(-1, "batched gemm: causal reduction needs K >= M");
+    return dispatch_major<256, 5, 2>(a, p, st, &tmC, a_rows_total, b_rows_total);
 }
 
 }  // namespace b200
@@ -459,21 +630,32 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     B200_REQUIRE(!a->bias || aligned16(a->bias), "gemm: bias must be 16B aligned");
     B200_REQUIRE(!a->aux_out || aligned16(a->aux_out), "gemm: aux_out must be 16B aligned");
     GemmParams p;
-    p.M = a->M, p.N = a->N, p.K = a->K;
-    p.C = a->C, p.ldc = a->ldc, p.c_fp32 = a->c_fp32, p.accumulate = a->accumulate;
-    p.bias = a->bias;
-    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
-    p.ldr = a->ldr;
-    p.gelu = a->gelu;
-    p.alpha_dev = a->alpha_dev;
-    p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
-    p.dgelu_in = static_cast<const __nv_bfloat16*>(a->dgelu_in);
+    fill_params(a, p);
     static const int dbg = getenv("B200_GEMM_DEBUG") ? atoi(getenv("B200_GEMM_DEBUG")) : 0;
+    static const int force_cg = getenv("B200_GEMM_CG") ? atoi(getenv("B200_GEMM_CG")) : 0;  // perf triage: 1 = single-CTA engine
     p.debug = dbg;
     p.tma_store = (!a->c_fp32 && !a->accumulate && !(dbg & 64)) ? 1 : 0;
     B200_REQUIRE(!a->aux_out || a->gelu, "gemm: aux_out is the pre-GELU output and needs gelu=1");
     cudaStream_t st = as_stream(stream);
-    // 128 x 256 tiles when N is wide enough to fill them; 128 x 128 otherwise
-    if (a->N > 128) return dispatch_major<256, 4>(a, p, st);
-    return dispatch_major<128, 6>(a, p, st);
+    // CTA pairs on 256 x 256 tiles when the problem fills them; 128 x 256 / 128 x 128 single-CTA tiles otherwise
+    if (a->N > 128 && a->M > 128 && force_cg != 1) {
+        if (a->c_fp32 && a->accumulate && !a->bias && !a->residual && !a->dgelu_in && !a->gelu && !(dbg & 128)) {
+            // wgrad: few, very long tiles. Cut the reduction so that the work units fill whole waves of CTA pairs
+            // (e.g. 256 tiles on 74 pairs: 3.46 waves -> split 2 -> 6.92); partial sums meet in C through red.add.
+            const int tiles = ((a->M + 255) / 256) * ((a->N + 255) / 256);
+            const int workers = num_sms() / 2;
+            const int num_kb = (a->K + GEMM_BK - 1) / GEMM_BK;
+            int best = 1;
+            double best_eff = 0.0;
+            for (int sk = 1; sk <= 8 && num_kb / sk >= 32; ++sk) {
+                const double waves = static_cast<double>(tiles) * sk / workers;
+                const double eff = waves / static_cast<double>(static_cast<int64_t>(waves + 0.999999));
+                if (eff > best_eff + 0.02) best_eff = eff, best = sk;
+            }
+            p.split_k = best;
+        }
+        return dispatch_major<256, 5, 2>(a, p, st);
+    }
+    if (a->N > 128) return dispatch_major<256, 4, 1>(a, p, st);
+    return dispatch_major<128, 6, 1>(a, p, st);
 }

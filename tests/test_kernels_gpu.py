@@ -174,8 +174,8 @@ def K_gemm(*a, **k):
     return K.gemm(*a, **k)
 
 
-def test_gemm_epilogues(dev):
-    M, N, Kd = 512, 1024, 512
+@pytest.mark.parametrize("M,N,Kd", [(512, 1024, 512), (200, 136, 328), (128, 256, 64), (300, 520, 192)])
+def test_gemm_epilogues(dev, M, N, Kd):
     g = torch.Generator(device="cpu").manual_seed(5)
     A = torch.randn(M, Kd, generator=g).to(dev).to(BF16)
     W = (torch.randn(N, Kd, generator=g) * 0.05).to(dev).to(BF16)
