@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 4
+#define B200PT_ABI_VERSION 5
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
@@ -145,6 +145,12 @@ typedef struct b200_attn_args {
     void* dv;                 /* same layout as q/k/v (dqkv_* strides) */
     int64_t dqkv_row_stride;
     int64_t dqkv_head_stride;
+    /* backward, head_dim 256 only (nullable): two bf16 scratch buffers [B*H, S, S]. When both are given and S % 256 == 0
+     * the dQ pass also stores its P and dS tiles there and dV = P^T dO, dK = scale dS^T Q run as batched causal GEMMs
+     * on the CTA-pair tensor-core engine; otherwise dK/dV are recomputed in a second fused pass. The causal path only
+     * ever writes the lower block triangle; the buffers need no initialisation. */
+    void* p_scratch;
+    void* ds_scratch;
 } b200_attn_args;
 int b200_attention_fwd(const b200_attn_args* args, b200_stream_t stream);
 int b200_attention_bwd(const b200_attn_args* args, b200_stream_t stream);

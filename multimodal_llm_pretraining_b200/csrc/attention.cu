@@ -16,6 +16,7 @@
 //   For D = 256 the dK/dV accumulators (2 x 256 columns) exceed TMEM next to S^T/dP^T, so the DKV pass is split over two
 //   CTAs that each own 128 of the 256 output columns.
 #include <math.h>
+#include <stdlib.h>
 
 #include "api.h"
 #include "common.cuh"
@@ -37,6 +38,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// perf triage (B200_ATTN_TRACE=1): per-event SM clock stamps of CTA (0,0,0) of the head_dim-256 score pass
+__device__ unsigned long long g_attn_trace[8192];
+__device__ __forceinline__ void trace_evt(bool on, int slot) {
+    if (on) g_attn_trace[slot] = clock64();
+}
+
 struct AttnParams {
     int B, S, H, D;
     int causal;
@@ -50,6 +57,9 @@ struct AttnParams {
     __nv_bfloat16* dk;
     __nv_bfloat16* dv;
     int64_t dqkv_row_stride, dqkv_head_stride;
+    __nv_bfloat16* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
+    int trace;
+    __nv_bfloat16* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
 };
 
 // write 8 consecutive bf16 (one 16-byte chunk, index cc along the row) of row r into a [128 x 64*nsub] K-major
@@ -135,15 +145,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 4) {
-        // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        // ---------------------------------------------------------------- TMA producer (one elected thread)
+        if (elect_one()) {
             mbar_expect_tx(q_full, L::Q_BYTES);
             for (int c = 0; c < NSUB; ++c) tma_load_2d(sQ + c * 16384, &tmQ, q_full, col0 + c * 64, row_base + q0);
-        }
-        for (int j = 0; j < n_blocks; ++j) {
-            const int s = j % STAGES;
-            mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
-            if (lane == 0) {
+            for (int j = 0; j < n_blocks; ++j) {
+                const int s = j % STAGES;
+                mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], L::KV_BYTES);
                 for (int c = 0; c < NSUB; ++c)
                     tma_load_2d(sK + s * L::KV_BYTES + c * (BN * 128), &tmK, &k_full[s], col0 + c * 64, row_base + j * BN);
@@ -151,49 +159,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int c = 0; c < NSUB; ++c)
                     tma_load_2d(sV + s * L::KV_BYTES + c * (BN * 128), &tmV, &v_full[s], col0 + c * 64, row_base + j * BN);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp == 5) {
-        // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, false, false);  // S = Q K^T: both K-major
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);    // O = P V  : V is MN-major (d contiguous)
-        auto issue_s = [&](int j) {
-            const int s = j % STAGES;
-            mbar_wait(&k_full[s], (j / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + s * L::KV_BYTES);
+        // ---------------------------------------------------------------- MMA issuer (one elected thread: the compiler
+        // keeps descriptors in uniform registers and issues UTCHMMA back to back; a lane==0 branch costs ~17 instructions
+        // of register->uniform broadcast per MMA, more than a 128x64x16 MMA takes to execute)
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, false, false);  // S = Q K^T: both K-major
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);    // O = P V  : V is MN-major (d contiguous)
+            const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t p_desc = umma_desc_sw128(smem_u32(sP), 16, 1024);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), BN * 128, 1024);
+            auto issue_s = [&](int j) {
+                const int s = j % STAGES;
+                mbar_wait(&k_full[s], (j / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((s * L::KV_BYTES) >> 4);
+                const uint32_t d_s = tmem + TM_S + (j & 1) * BN;
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(qa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_desc_sw128(ka + (kk >> 2) * (BN * 128) + (kk & 3) * 32, 16, 1024);
-                    umma_ss(tmem + TM_S + (j & 1) * BN, ad, bd, idesc_s, kk != 0);
+                    const uint64_t ad = q_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                    const uint64_t bd = kd + static_cast<uint64_t>(((kk >> 2) * (BN * 128) + (kk & 3) * 32) >> 4);
+                    umma_ss(d_s, ad, bd, idesc_s, kk != 0);
                 }
                 tc_commit(&s_full[j & 1]);
-            }
-            __syncwarp();
-        };
-        mbar_wait(q_full, 0);
-        issue_s(0);
-        for (int j = 0; j < n_blocks; ++j) {
-            const int s = j % STAGES;
-            if (j + 1 < n_blocks) issue_s(j + 1);
-            mbar_wait(p_ready, j & 1);
-            mbar_wait(&v_full[s], (j / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t pa = smem_u32(sP), va = smem_u32(sV + s * L::KV_BYTES);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int s = j % STAGES;
+                if (j + 1 < n_blocks) issue_s(j + 1);
+                mbar_wait(p_ready, j & 1);
+                mbar_wait(&v_full[s], (j / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * L::KV_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BN / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_desc_sw128(va + kk * 2048, BN * 128, 1024);
+                    const uint64_t ad = p_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                    const uint64_t bd = vd + static_cast<uint64_t>((kk * 2048) >> 4);
                     umma_ss(tmem + TM_O, ad, bd, idesc_o, (j | kk) != 0);
                 }
                 tc_commit(&kv_empty[s]);
                 tc_commit(o_done);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // ---------------------------------------------------------------- softmax warps: thread = query row
         const int r = warp * 32 + lane;
@@ -420,18 +432,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 4) {
-        // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        // ---------------------------------------------------------------- TMA producer (one elected thread)
+        if (elect_one()) {
             mbar_expect_tx(r_full, 2 * L::R_BYTES);
             for (int c = 0; c < NSUB; ++c) {
                 tma_load_2d(sR1 + c * 16384, &tmR1, r_full, col0 + c * 64, row_base + r0);
                 tma_load_2d(sR2 + c * 16384, &tmR2, r_full, (DKV ? col0 : col0_do) + c * 64, row_base + r0);
             }
-        }
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t % STAGES;
-            mbar_wait(&t_empty[s], ((t / STAGES) & 1) ^ 1);
-            if (lane == 0) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % STAGES;
+                mbar_wait(&t_empty[s], ((t / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&t_full[s], 2 * L::T_BYTES);
                 const int row = row_base + (t_begin + t) * BT;
                 for (int c = 0; c < NSUB; ++c) {
@@ -439,68 +449,68 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                     tma_load_2d(sT2 + s * L::T_BYTES + c * 8192, &tmT2, &t_full[s], (DKV ? col0_do : col0) + c * 64, row);
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp == 5) {
-        // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
-        constexpr uint32_t idesc_acc = umma_idesc_bf16(128, DKV ? DH : D, false, true);
-        auto issue_scores = [&](int t) {
-            const int s = t % STAGES;
-            mbar_wait(&t_full[s], (t / STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t r1 = smem_u32(sR1), r2 = smem_u32(sR2);
-                const uint32_t t1 = smem_u32(sT1 + s * L::T_BYTES), t2 = smem_u32(sT2 + s * L::T_BYTES);
+        // ---------------------------------------------------------------- MMA issuer (one elected thread)
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
+            constexpr uint32_t idesc_acc = umma_idesc_bf16(128, DKV ? DH : D, false, true);
+            const uint64_t r1_desc = umma_desc_sw128(smem_u32(sR1), 16, 1024);
+            const uint64_t r2_desc = umma_desc_sw128(smem_u32(sR2), 16, 1024);
+            const uint64_t t1k_desc0 = umma_desc_sw128(smem_u32(sT1), 16, 1024);    // streamed tiles as K-major B (scores)
+            const uint64_t t2k_desc0 = umma_desc_sw128(smem_u32(sT2), 16, 1024);
+            const uint64_t t1m_desc0 = umma_desc_sw128(smem_u32(sT1), 8192, 1024);  // ... and as MN-major B (accumulate)
+            const uint64_t t2m_desc0 = umma_desc_sw128(smem_u32(sT2), 8192, 1024);
+            const uint64_t a1_desc = umma_desc_sw128(smem_u32(sA1), 16, 1024);
+            const uint64_t a2_desc = umma_desc_sw128(smem_u32(sA2), 16, 1024);
+            auto issue_scores = [&](int t) {
+                const int s = t % STAGES;
+                mbar_wait(&t_full[s], (t / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t soff = static_cast<uint64_t>((s * L::T_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(r1 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_desc_sw128(t1 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                    const uint64_t ad = r1_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                    const uint64_t bd = t1k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4);
                     umma_ss(tmem + TM_S, ad, bd, idesc_s, kk != 0);
                 }
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(r2 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_desc_sw128(t2 + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                    const uint64_t ad = r2_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                    const uint64_t bd = t2k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4);
                     umma_ss(tmem + TM_DP, ad, bd, idesc_s, kk != 0);
                 }
                 tc_commit(s_full);
-            }
-            __syncwarp();
-        };
-        mbar_wait(r_full, 0);
-        if (n_tiles > 0) issue_scores(0);
-        for (int t = 0; t < n_tiles; ++t) {
-            const int s = t % STAGES;
-            mbar_wait(a_ready, t & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2);
-                const uint32_t t1 = smem_u32(sT1 + s * L::T_BYTES), t2 = smem_u32(sT2 + s * L::T_BYTES);
-                const uint32_t boff = half * (DH / 64) * 8192;  // first 64-column sub-tile of this CTA's output half
+            };
+            mbar_wait(r_full, 0);
+            if (n_tiles > 0) issue_scores(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % STAGES;
+                mbar_wait(a_ready, t & 1);
+                tc_fence_after();
+                const uint64_t soff = static_cast<uint64_t>((s * L::T_BYTES) >> 4);
+                const uint64_t boff = soff + static_cast<uint64_t>((half * (DH / 64) * 8192) >> 4);  // this CTA's output half
 #pragma unroll
                 for (int kk = 0; kk < BT / 16; ++kk) {
                     if (!DKV) {
                         // dQ += dS (K-major A) * K_j (MN-major B)
-                        const uint64_t ad = umma_desc_sw128(a1 + kk * 32, 16, 1024);
-                        const uint64_t bd = umma_desc_sw128(t1 + kk * 2048, 8192, 1024);
-                        umma_ss(tmem + TM_ACC1, ad, bd, idesc_acc, (t | kk) != 0);
+                        umma_ss(tmem + TM_ACC1, a1_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                                t1m_desc0 + soff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
                     } else {
                         // dV += P^T * dO_i ; dK += dS^T * Q_i
-                        const uint64_t ad1 = umma_desc_sw128(a1 + kk * 32, 16, 1024);
-                        const uint64_t bd1 = umma_desc_sw128(t2 + boff + kk * 2048, 8192, 1024);
-                        umma_ss(tmem + TM_ACC1, ad1, bd1, idesc_acc, (t | kk) != 0);
-                        const uint64_t ad2 = umma_desc_sw128(a2 + kk * 32, 16, 1024);
-                        const uint64_t bd2 = umma_desc_sw128(t1 + boff + kk * 2048, 8192, 1024);
-                        umma_ss(tmem + TM_ACC2, ad2, bd2, idesc_acc, (t | kk) != 0);
+                        umma_ss(tmem + TM_ACC1, a1_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                                t2m_desc0 + boff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
+                        umma_ss(tmem + TM_ACC2, a2_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                                t1m_desc0 + boff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
                     }
                 }
                 tc_commit(&t_empty[s]);
                 tc_commit(acc_done);
+                if (t + 1 < n_tiles) issue_scores(t + 1);
             }
-            __syncwarp();
-            if (t + 1 < n_tiles) issue_scores(t + 1);
         }
+        __syncwarp();
     } else {
         // ---------------------------------------------------------------- compute warps: thread = resident row
         const int r = warp * 32 + lane;
@@ -557,6 +567,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 const uint4 dsv = make_uint4(f2_to_bf2(ds[0], ds[1]), f2_to_bf2(ds[2], ds[3]), f2_to_bf2(ds[4], ds[5]), f2_to_bf2(ds[6], ds[7]));
                 if (!DKV) {
                     st_operand_chunk(sA1, r, cc, dsv);
+                    if (p.p_out != nullptr && r_idx < p.S) {
+                        // thread = query row: 16 B of P and of dS per chunk, 128 contiguous bytes per row and tile
+                        const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + c0 + cc * 8;
+                        st_v4(p.p_out + off, make_uint4(f2_to_bf2(pv[0], pv[1]), f2_to_bf2(pv[2], pv[3]), f2_to_bf2(pv[4], pv[5]), f2_to_bf2(pv[6], pv[7])));
+                        st_v4(p.ds_out + off, dsv);
+                    }
                 } else {
                     st_operand_chunk(sA1, r, cc, make_uint4(f2_to_bf2(pv[0], pv[1]), f2_to_bf2(pv[2], pv[3]), f2_to_bf2(pv[4], pv[5]), f2_to_bf2(pv[6], pv[7])));
                     st_operand_chunk(sA2, r, cc, dsv);
@@ -566,6 +582,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
+        }
+        if (!DKV && p.p_out != nullptr && p.causal && (blk & 1) == 0 && r_idx < p.S && r0 + 128 < p.S) {
+            // The batched dK/dV GEMMs work on 256-key tiles and start their reduction at the tile's first query row, so
+            // for the first 128 queries of such a tile they also read keys [r0+128, r0+256): never visited by this
+            // causal pass -> must hold zeros.
+            const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + r0 + 128;
+            const int n = min(128, p.S - (r0 + 128));
+            for (int c = 0; c < n; c += 8) {
+                st_v4(p.p_out + off + c, make_uint4(0, 0, 0, 0));
+                st_v4(p.ds_out + off + c, make_uint4(0, 0, 0, 0));
+            }
         }
         // ---- epilogue
         if (n_tiles > 0) {
@@ -617,6 +644,361 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     }
 }
 
+// =================================================================================================================
+// backward, head_dim 256: score pass
+// =================================================================================================================
+// Per CTA: 128 query rows of one (b, h); loops over 64-key tiles. Per tile:
+//   S = Q K^T (Q bf16 in TMEM as the A operand: no smem, no smem bandwidth), dP = dO V^T, P = exp2(S*c - lse), dS = P (dP - delta)
+//   -> bf16 P and dS tiles: TMA-stored to the [B*H, S, S] scratch for the batched dV / dK GEMMs; dS is also the A operand of
+//   dQ += dS K (fp32 in TMEM, 256 columns).
+// Shared memory (224 KB): dO resident 64 KB | K x2 64 KB | V x2 64 KB | dS 16 KB | P 16 KB. Keeping Q out of shared memory
+// is what makes room for double-buffered K/V: with one stage the TMA latency of every tile sat on the critical path.
+// TMEM (512 columns): dQ [0,256) | S [256,320) | dP [320,384) | Q bf16 [384,512).
+// Pipeline: scores of tile t+1 are issued as soon as the compute warps have pulled tile t into registers, so tensor work
+// of tile t+1 overlaps the exp/mul work of tile t; dQ of tile t follows when its dS tile is in shared memory.
+struct Dq256Smem {
+    static constexpr uint32_t OFF_DO = 0;
+    static constexpr uint32_t OFF_K = 65536;
+    static constexpr uint32_t OFF_V = OFF_K + 2 * 32768;
+    static constexpr uint32_t OFF_DS = OFF_V + 2 * 32768;
+    static constexpr uint32_t OFF_P = OFF_DS + 16384;
+    static constexpr uint32_t OFF_BAR = OFF_P + 16384;
+    static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP,
+                      const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDQ,
+                      const __nv_bfloat16* __restrict__ qptr, int64_t q_row_stride, const AttnParams p) {
+    using L = Dq256Smem;
+    constexpr int D = 256, BT = 64, NSUB = 4;
+    constexpr uint32_t TM_DQ = 0, TM_S = 256, TM_DP = 320, TM_Q = 384;
+    constexpr uint32_t KV_BYTES = 32768;  // one 64-row K (or V) tile: 4 sub-tiles of 64 rows x 128 B
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sDO = smem + L::OFF_DO;
+    uint8_t* sK = smem + L::OFF_K;
+    uint8_t* sV = smem + L::OFF_V;
+    uint8_t* sDS = smem + L::OFF_DS;
+    uint8_t* sP = smem + L::OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* do_full = bars;        // 1
+    uint64_t* q_ready = bars + 1;    // 1 (4 warp arrivals)
+    uint64_t* slot_full = bars + 2;   // 4: the K / V ring (see kslot / vslot)
+    uint64_t* slot_empty = bars + 6;  // 4
+    uint64_t* s_full = bars + 10;    // 1
+    uint64_t* s_free = bars + 11;    // 1 (4 warp arrivals)
+    uint64_t* a_ready = bars + 12;   // 1
+    uint64_t* dq_done = bars + 13;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int r0 = blk * 128;
+    const int col0 = h * static_cast<int>(p.qkv_head_stride);
+    const int col0_do = h * static_cast<int>(p.o_head_stride);
+    const int row_base = b * p.S;
+    const int n_tiles = ((p.causal ? min(p.S, r0 + 128) : p.S) + BT - 1) / BT;
+    const int zrow = (b * p.H + h) * p.S;  // first row of this head's [S, S] score matrix in the scratch
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmDO);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmP);
+        tma_prefetch_desc(&tmDS);
+        tma_prefetch_desc(&tmDQ);
+        mbar_init(do_full, 1);
+        mbar_init(q_ready, 4);
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&slot_full[s], 1);
+            mbar_init(&slot_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 4);
+        mbar_init(a_ready, 1);
+        mbar_init(dq_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // Four 32 KB slots hold the K and V tiles. A V tile is dead once dP of its tile is done (early), a K tile only after
+    // dQ (late); a TMA load takes ~2000 clocks. So tile t+2's K goes into the slot V_t just left (2 tiles of lead) and its
+    // V into K_t's slot: each slot is used once every two tiles, alternating roles.
+    auto kslot = [](int t) { return ((t & 1) << 1) | ((t >> 1) & 1); };  // 0,2,1,3
+    auto vslot = [](int t) { return (((t & 1) << 1) | ((t >> 1) & 1)) ^ 1; };  // 1,3,0,2
+    uint8_t* sKV = sK;  // slots are contiguous: sV == sK + 2 * KV_BYTES
+
+    if (warp == 4) {
+        // ---------------------------------------------------------------- TMA producer
+        if (elect_one()) {
+            mbar_expect_tx(do_full, 65536);
+            for (int c = 0; c < NSUB; ++c) tma_load_2d(sDO + c * 16384, &tmDO, do_full, col0_do + c * 64, row_base + r0);
+            // K and V tiles are loaded in tile order each, but whichever of the two next slots comes free first is served first
+            // (a parity wait cannot tell "use u-1 not even issued" from "use u-1 released": a slot's uses are tried strictly in
+            // order, tracked by one 8-bit counter per slot)
+            int next_k = 0, next_v = 0;
+            uint32_t uses = 0;
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_k < n_tiles || next_v < n_tiles) {
+                bool progressed = false;
+#pragma unroll
+                for (int is_k = 1; is_k >= 0; --is_k) {
+                    const int t = is_k ? next_k : next_v;
+                    if (t >= n_tiles) continue;
+                    const int slot = is_k ? kslot(t) : vslot(t);
+                    if (((uses >> (8 * slot)) & 0xff) != static_cast<uint32_t>((t >> 1) & 0xff)) continue;
+                    if (!mbar_try_wait(&slot_empty[slot], ((t >> 1) & 1) ^ 1)) continue;
+                    uses += 1u << (8 * slot);
+                    mbar_expect_tx(&slot_full[slot], KV_BYTES);
+                    for (int c = 0; c < NSUB; ++c)
+                        tma_load_2d(sKV + slot * KV_BYTES + c * 8192, is_k ? &tmK : &tmV, &slot_full[slot], col0 + c * 64, row_base + t * BT);
+                    if (is_k) ++next_k; else ++next_v;
+                    progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention score pass producer stalled (block %d,%d,%d k %d v %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, next_k, next_v);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
+            constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, false, true);
+            const uint64_t do_desc = umma_desc_sw128(smem_u32(sDO), 16, 1024);
+            const uint64_t kk_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);    // K tile as K-major B (scores)
+            const uint64_t km_desc0 = umma_desc_sw128(smem_u32(sK), 8192, 1024);  // K tile as MN-major B (dQ += dS K)
+            const uint64_t ds_desc = umma_desc_sw128(smem_u32(sDS), 16, 1024);
+            auto issue_s = [&](int t) {  // S_t = Q K_t^T (A = Q from TMEM: 16 bf16 = 8 columns per k step)
+                const uint64_t koff = static_cast<uint64_t>((kslot(t) * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ts(tmem + TM_S, tmem + TM_Q + kk * 8, kk_desc0 + koff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4),
+                            idesc_s, kk != 0);
+            };
+            auto issue_dp = [&](int t) {  // dP_t = dO V_t^T, then the V slot is free and the scores are complete
+                const int vs = vslot(t);
+                const uint64_t voff = static_cast<uint64_t>((vs * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tmem + TM_DP, do_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                            kk_desc0 + voff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
+                tc_commit(&slot_empty[vs]);
+                tc_commit(s_full);
+            };
+            auto issue_dq = [&](int t) {  // dQ += dS_t K_t, then the K slot is free
+                const uint64_t soff = static_cast<uint64_t>((kslot(t) * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BT / 16; ++kk)
+                    umma_ss(tmem + TM_DQ, ds_desc + static_cast<uint64_t>((kk * 32) >> 4), km_desc0 + soff + static_cast<uint64_t>((kk * 2048) >> 4),
+                            idesc_dq, (t | kk) != 0);
+                tc_commit(&slot_empty[kslot(t)]);
+                tc_commit(dq_done);
+            };
+            mbar_wait(q_ready, 0);
+            mbar_wait(do_full, 0);
+            mbar_wait(&slot_full[kslot(0)], 0);
+            tc_fence_after();
+            issue_s(0);
+            mbar_wait(&slot_full[vslot(0)], 0);
+            tc_fence_after();
+            issue_dp(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                // Three things to issue, in whatever order their inputs arrive: S_{t+1} (compute warps pulled tile t out of
+                // TMEM, K_{t+1} landed), then dP_{t+1} (V_{t+1} landed), and dQ_t (dS_t is in shared memory). Waiting for them
+                // in a fixed order delays dQ_t behind a V load, which delays the slot that very load family needs next.
+                bool need_s = t + 1 < n_tiles, need_dp = need_s, need_dq = true;
+                const uint32_t ph1 = ((t + 1) >> 1) & 1;
+                const uint64_t t_start = globaltimer_ns();
+                uint32_t spins = 0;
+                while (need_s || need_dp || need_dq) {
+                    if (((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > B200_MBAR_TIMEOUT_NS) {
+                        printf("b200pt: attention score pass stalled (block %d,%d,%d tile %d: s %d dp %d dq %d)\n", blockIdx.x, blockIdx.y,
+                               blockIdx.z, t, need_s, need_dp, need_dq);
+                        __trap();
+                    }
+                    if (need_s && mbar_try_wait(s_free, t & 1) && mbar_try_wait(&slot_full[kslot(t + 1)], ph1)) {
+                        tc_fence_after();
+                        trace_evt(tr, 16 * t + 0);
+                        issue_s(t + 1);
+                        need_s = false;
+                    }
+                    if (!need_s && need_dp && mbar_try_wait(&slot_full[vslot(t + 1)], ph1)) {
+                        tc_fence_after();
+                        issue_dp(t + 1);
+                        trace_evt(tr, 16 * t + 1);
+                        need_dp = false;
+                    }
+                    if (need_dq && mbar_try_wait(a_ready, t & 1)) {
+                        tc_fence_after();
+                        trace_evt(tr, 16 * t + 2);
+                        issue_dq(t);
+                        trace_evt(tr, 16 * t + 3);
+                        need_dq = false;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- compute warps: thread = query row = TMEM lane
+        const int r = warp * 32 + lane;
+        const int r_idx = r0 + r;
+        const bool row_ok = r_idx < p.S;
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const float sl2 = p.scale * LOG2E_F;
+        const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.S;
+        // rows beyond S: lse = +inf makes every P (and dS) of the row exactly 0
+        const float neg_lse2 = row_ok ? -p.lse[stat_base + r_idx] * LOG2E_F : -INFINITY;
+        const float my_delta = row_ok ? p.delta[stat_base + r_idx] : 0.f;
+        const int S_ = p.S;
+        const bool causal_ = p.causal != 0;
+        {
+            // Q row -> TMEM (bf16 pairs, 128 columns). All 32 loads are issued before the first store: one HBM round trip.
+            const __nv_bfloat16* qrow = qptr + static_cast<size_t>(row_base + (row_ok ? r_idx : r0)) * q_row_stride + col0;
+            uint4 u[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = row_ok ? ld_nc_v4(qrow + i * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i * 4 + 0] = u[c * 8 + i].x, v[i * 4 + 1] = u[c * 8 + i].y, v[i * 4 + 2] = u[c * 8 + i].z, v[i * 4 + 3] = u[c * 8 + i].w;
+                tmem_st_32x32(lane_addr + TM_Q + c * 32, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int c0 = t * BT;
+            const bool tr0 = tr && threadIdx.x == 0;
+            trace_evt(tr0, 16 * t + 8);
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            trace_evt(tr0, 16 * t + 9);
+            uint32_t sv[64], dv[64];
+            tmem_ld_32x32(lane_addr + TM_S, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32(lane_addr + TM_S + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_32x32(lane_addr + TM_DP, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
+            tmem_ld_32x32(lane_addr + TM_DP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);
+            trace_evt(tr0, 16 * t + 10);
+            // masking is branch-free inside the tile (scores -> -inf, exp2 -> 0) and skipped for tiles below the diagonal
+            const bool need_mask = (c0 + BT > S_) || (causal_ && c0 + BT - 1 > r0);
+            if (need_mask) {
+                const int lim = causal_ ? min(S_ - 1, r_idx) : S_ - 1;  // last visible key of this row
+#pragma unroll
+                for (int i = 0; i < 64; ++i) sv[i] = (c0 + i > lim) ? 0xff800000u : sv[i];
+            }
+            uint32_t pk[32], dk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float pe0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, neg_lse2));
+                const float pe1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, neg_lse2));
+                pk[i] = f2_to_bf2(pe0, pe1);
+                dk[i] = f2_to_bf2(pe0 * (__uint_as_float(dv[2 * i]) - my_delta), pe1 * (__uint_as_float(dv[2 * i + 1]) - my_delta));
+            }
+            // the P / dS tiles of the previous iteration must have been consumed: dS by the dQ MMAs, both by the TMA stores
+            trace_evt(tr0, 16 * t + 11);
+            if (t > 0) mbar_wait(dq_done, (t - 1) & 1);
+            trace_evt(tr0, 16 * t + 12);
+            if (threadIdx.x == 0) tma_store_wait_read<0>();
+            trace_evt(tr0, 16 * t + 13);
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                st_shared_v4(sP + sw128_offset(r, cc), make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]));
+                st_shared_v4(sDS + sw128_offset(r, cc), make_uint4(dk[cc * 4], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]));
+            }
+            fence_proxy_async_smem();
+            trace_evt(tr0, 16 * t + 14);
+            named_bar_sync(1, 128);
+            trace_evt(tr0, 16 * t + 15);
+            if (threadIdx.x == 0) {
+                mbar_arrive(a_ready);
+                tma_store_2d(&tmP, sP, c0, zrow + r0);
+                tma_store_2d(&tmDS, sDS, c0, zrow + r0);
+                tma_store_commit();
+            }
+        }
+        // ---- the dK/dV GEMMs reduce over queries starting at the first row of their 256-key tile: for the first 128
+        // queries of such a tile they read keys [r0+128, r0+256), which this causal pass never visits -> store zeros.
+        const bool zero_quad = p.causal && (blk & 1) == 0 && r0 + 128 < p.S;
+        if (threadIdx.x == 0) tma_store_wait_read<0>();
+        if (n_tiles > 0) {
+            mbar_wait(dq_done, (n_tiles - 1) & 1);
+            tc_fence_after();
+        }
+        named_bar_sync(1, 128);
+        if (zero_quad) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) st_shared_v4(sP + sw128_offset(r, cc), make_uint4(0, 0, 0, 0));
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (threadIdx.x == 0) {
+                for (int c = r0 + 128; c < min(p.S, r0 + 256); c += 64) {
+                    tma_store_2d(&tmP, sP, c, zrow + r0);
+                    tma_store_2d(&tmDS, sP, c, zrow + r0);
+                }
+                tma_store_commit();
+            }
+        }
+        // ---- epilogue: dQ * scale -> bf16, staged through the (now idle) dO tile, TMA-stored
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            if (n_tiles > 0) {
+                tmem_ld_32x32(lane_addr + TM_DQ + c * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * p.scale, __uint_as_float(v[g * 8 + 1]) * p.scale);
+                o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * p.scale, __uint_as_float(v[g * 8 + 3]) * p.scale);
+                o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * p.scale, __uint_as_float(v[g * 8 + 5]) * p.scale);
+                o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * p.scale, __uint_as_float(v[g * 8 + 7]) * p.scale);
+                st_shared_v4(sDO + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + g), o);
+            }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+            for (int c = 0; c < NSUB; ++c) tma_store_2d(&tmDQ, sDO + c * 16384, col0 + c * 64, row_base + r0);
+            tma_store_commit();
+            tma_store_wait_all<0>();  // shared memory must outlive the bulk stores reading it
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
@@ -649,6 +1031,9 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.dk = static_cast<__nv_bfloat16*>(a->dk);
     p.dv = static_cast<__nv_bfloat16*>(a->dv);
     p.dqkv_row_stride = a->dqkv_row_stride, p.dqkv_head_stride = a->dqkv_head_stride;
+    p.p_out = nullptr, p.ds_out = nullptr;
+    static const int tr = getenv("B200_ATTN_TRACE") ? 1 : 0;
+    p.trace = tr;
     return p;
 }
 
@@ -676,7 +1061,7 @@ static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
 }
 
 template <int D, int DH, int STAGES, bool DKV>
-static int launch_bwd(const b200_attn_args* a, cudaStream_t st) {
+static int launch_bwd(const b200_attn_args* a, cudaStream_t st, bool store_scores = false) {
     using L = BwdSmem<D, STAGES, DKV>;
     static_assert(L::TOTAL <= 232448, "backward smem budget");
     CUtensorMap r1, r2, t1, t2;
@@ -697,13 +1082,74 @@ static int launch_bwd(const b200_attn_args* a, cudaStream_t st) {
     auto kern = attn_bwd_kernel<D, DH, STAGES, DKV>;
     if ((rc = set_smem(kern, L::TOTAL, "attention_bwd"))) return rc;
     dim3 grid(((a->S + 127) / 128) * (DKV ? D / DH : 1), a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(r1, r2, t1, t2, make_params(a));
+    AttnParams prm = make_params(a);
+    if (store_scores) {
+        prm.p_out = static_cast<__nv_bfloat16*>(a->p_scratch);
+        prm.ds_out = static_cast<__nv_bfloat16*>(a->ds_scratch);
+    }
+    kern<<<grid, 192, L::TOTAL, st>>>(r1, r2, t1, t2, prm);
     return check_launch(DKV ? "attention_bwd_dkv" : "attention_bwd_dq");
+}
+
+static int launch_bwd_dq256(const b200_attn_args* a, cudaStream_t st) {
+    using L = Dq256Smem;
+    static_assert(L::TOTAL <= 232448, "dq256 smem budget");
+    CUtensorMap tdo, tk, tv, tp, tds, tdq;
+    int rc;
+    b200_attn_args oa = *a;
+    if ((rc = qkv_tmap(&tdo, a->d_o, &oa, a->o_row_stride, a->o_head_stride, 128))) return rc;
+    if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    const uint64_t zs = static_cast<uint64_t>(a->B) * a->H * a->S;
+    if ((rc = make_tmap_bf16_2d(&tp, a->p_scratch, a->S, zs, a->S, 64, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tds, a->ds_scratch, a->S, zs, a->S, 64, 128))) return rc;
+    if ((rc = qkv_tmap(&tdq, a->dq, a, a->dqkv_row_stride, a->dqkv_head_stride, 128))) return rc;
+    auto kern = attn_bwd_dq256_kernel;
+    if ((rc = set_smem(kern, L::TOTAL, "attention_bwd_dq256"))) return rc;
+    dim3 grid((a->S + 127) / 128, a->H, a->B);
+    kern<<<grid, 192, L::TOTAL, st>>>(tdo, tk, tv, tp, tds, tdq, static_cast<const __nv_bfloat16*>(a->q), a->qkv_row_stride, make_params(a));
+    return check_launch("attention_bwd_dq256");
+}
+
+// dV = P^T dO and dK = scale * dS^T Q over the materialised score tiles: two batched (B*H problems) causal GEMMs on the
+// CTA-pair engine (gemm.cu). A = scratch [B*H*S (query i), S (key j)] read as [K, M]; B = dO / Q rows read as [K, N].
+int gemm_batched_pair(const b200_gemm_args* a, int nb, int nh, const int (&offs)[12], int causal_k, float alpha,
+                      uint64_t a_rows_total, uint64_t b_rows_total, const CUtensorMap& tmC, cudaStream_t st);  // gemm.cu
+
+static int dkv_from_scores(const b200_attn_args* a, cudaStream_t st) {
+    const int S = a->S, H = a->H, D = a->D;
+    for (int which = 0; which < 2; ++which) {  // 0: dV from P and dO, 1: dK from dS and Q
+        b200_gemm_args g = {};
+        g.M = S, g.N = D, g.K = S;
+        g.A = which == 0 ? a->p_scratch : a->ds_scratch;
+        g.lda = S, g.a_mn = 1;
+        g.B = which == 0 ? a->d_o : a->q;
+        g.ldb = which == 0 ? a->o_row_stride : a->qkv_row_stride;
+        g.b_mn = 1;
+        g.C = which == 0 ? a->dv : a->dk;
+        g.ldc = a->dqkv_row_stride;
+        const int b_head = static_cast<int>(which == 0 ? a->o_head_stride : a->qkv_head_stride);
+        //                 a_k_b  a_k_h a_m_b a_m_h b_k_b b_k_h b_n_b b_n_h  c_m_b c_m_h c_n_b c_n_h
+        const int offs[12] = {H * S, S,    0,    0,    S,    0,    0,    b_head, S,    0,    0,    static_cast<int>(a->dqkv_head_stride)};
+        CUtensorMap tmC;
+        int rc = make_tmap_bf16_2d(&tmC, g.C, static_cast<uint64_t>(H - 1) * a->dqkv_head_stride + D, static_cast<uint64_t>(a->B) * S,
+                                   a->dqkv_row_stride, 64, 128);
+        if (rc) return rc;
+        rc = gemm_batched_pair(&g, a->B, H, offs, a->causal, which == 0 ? 1.0f : a->scale, static_cast<uint64_t>(a->B) * H * S,
+                               static_cast<uint64_t>(a->B) * S, tmC, st);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+// debug only (not part of include/b200pt.h): copies the score-pass trace buffer to the host
+extern "C" int b200_debug_attn_trace(unsigned long long* host, int n) {
+    return cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (n < 8192 ? n : 8192)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream) {
     int rc = check_common(a, "attention_fwd");
@@ -741,6 +1187,15 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
             if ((rc = launch_bwd<128, 128, 2, false>(a, st))) return rc;
             return launch_bwd<128, 128, 2, true>(a, st);
         default:
+            if (a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0) {
+                // head_dim 256: the dQ pass also writes its P / dS tiles; dK and dV become batched causal GEMMs (5 matmul
+                // units instead of the 9 a TMEM-limited fused dK/dV pass needs at this head size)
+                B200_REQUIRE(aligned16(a->p_scratch) && aligned16(a->ds_scratch), "attention_bwd: score scratch must be 16B aligned");
+                B200_REQUIRE(static_cast<int64_t>(a->B) * a->H * a->S < (1ll << 31), "attention_bwd: B*H*S too large for the score scratch path");
+                static const bool old_dq = getenv("B200_ATTN_OLD_DQ") != nullptr;  // perf triage only
+                if ((rc = old_dq ? launch_bwd<256, 256, 1, false>(a, st, true) : launch_bwd_dq256(a, st))) return rc;
+                return dkv_from_scores(a, st);
+            }
             if ((rc = launch_bwd<256, 256, 1, false>(a, st))) return rc;
             return launch_bwd<256, 128, 1, true>(a, st);
     }

@@ -308,6 +308,19 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 rows on the 128 lanes, 16-bit elements packed two per 32-bit
+// column, K-major) is read from tensor memory, so it costs no shared-memory bandwidth. Issued by ONE thread.
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+        : "memory");
+}
+
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (thread i of the warp gets lane base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(

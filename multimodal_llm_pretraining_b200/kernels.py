@@ -242,6 +242,19 @@ def _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale):
     return a
 
 
+USE_SCORE_SCRATCH = True
+_score_cache: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def _score_scratch(device, Z: int, S: int):
+    """Persistent bf16 [Z, S, S] P and dS scratch for the head_dim-256 backward (reused by every layer and step)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream, Z, S)
+    if key not in _score_cache:
+        _score_cache.clear()  # one shape at a time: these are GB-sized
+        _score_cache[key] = (torch.empty(Z, S, S, dtype=BF16, device=device), torch.empty(Z, S, S, dtype=BF16, device=device))
+    return _score_cache[key]
+
+
 def attention_fwd(q, k, v, causal, scale=None):
     """q,k,v: bf16 views [B,S,H,D] (any token/head strides, e.g. slices of a packed qkv buffer). Returns (o [B,S,H,D], lse [B,H,S])."""
     B, S, H, D = q.shape
@@ -265,10 +278,16 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None):
         _req(t.stride(1) == dq.stride(1) and t.stride(2) == dq.stride(2), "attention_bwd: dq,dk,dv must share strides")
     delta = torch.empty(B, H, S, dtype=F32, device=q.device)
     a.d_o, a.delta = ptr(d_o), ptr(delta)
+    n_launch = 3
+    if D == 256 and S % 256 == 0 and USE_SCORE_SCRATCH:
+        # head_dim 256: P / dS tiles go through HBM scratch and dK / dV become batched GEMMs (b200pt.h, b200_attn_args)
+        ps, dss = _score_scratch(q.device, B * H, S)
+        a.p_scratch, a.ds_scratch = ptr(ps), ptr(dss)
+        n_launch = 4
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
     a.dqkv_row_stride, a.dqkv_head_stride = dq.stride(1), dq.stride(2)
     check(_L(q).b200_attention_bwd(C.byref(a), stream_ptr()), "b200_attention_bwd")
-    _count(3)
+    _count(n_launch)
     return dq, dk, dv
 
 

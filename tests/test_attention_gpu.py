@@ -42,6 +42,8 @@ CASES = [
     (1, 136, 1, 256, True, True),
     (1, 2048, 2, 256, True, True),   # Pythia-1b head shape at full sequence length
     (1, 2048, 2, 64, True, True),
+    (2, 512, 2, 256, False, True),   # head_dim 256, bidirectional, score-scratch path
+    (2, 768, 3, 256, True, True),    # three 256-key tiles per head
 ]
 
 
@@ -96,3 +98,31 @@ def test_attention_large_logits(dev):
     ro, rlse = ref_attention(q.float(), k.float(), v.float(), False, D ** -0.5)
     assert rel_err(o, ro) <= 2e-2
     assert ((lse - rlse).abs() / rlse.abs().clamp_min(1)).max().item() <= 1e-2
+
+
+@pytest.mark.parametrize("use_scratch", [True, False])
+def test_attention_bwd_d256_scratch_paths_agree_and_ignore_stale_scratch(dev, use_scratch):
+    """head_dim 256: dK/dV via materialised P/dS + batched GEMMs (scratch poisoned with NaN first: every element the
+    GEMMs read must have been written by this call) vs the fused recompute pass."""
+    B, S, H, D = 2, 1024, 2, 256
+    _, q, k, v = make_qkv(B, S, H, D, True, dev, seed=11)
+    scale = D ** -0.5
+    o, lse = K.attention_fwd(q, k, v, True, scale)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    ro, _ = ref_attention(qf, kf, vf, True, scale)
+    d_o = torch.randn(B, S, H, D, generator=torch.Generator(device="cpu").manual_seed(5)).to(dev).to(BF16)
+    ro.backward(d_o.float())
+    old = K.USE_SCORE_SCRATCH
+    K.USE_SCORE_SCRATCH = use_scratch
+    try:
+        if use_scratch:
+            ps, dss = K._score_scratch(q.device, B * H, S)
+            ps.fill_(float("nan")), dss.fill_(float("nan"))
+        dbuf = torch.full((B, S, H, 3, D), float("nan"), device=dev, dtype=BF16)
+        dq, dk, dv = dbuf[:, :, :, 0], dbuf[:, :, :, 1], dbuf[:, :, :, 2]
+        K.attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, True, scale)
+    finally:
+        K.USE_SCORE_SCRATCH = old
+    for name, got, ref in (("dQ", dq, qf.grad), ("dK", dk, kf.grad), ("dV", dv, vf.grad)):
+        assert torch.isfinite(got.float()).all(), f"{name} has non-finite values"
+        assert rel_err(got, ref) <= 2e-2, f"{name} rel err {rel_err(got, ref):.3e}"
