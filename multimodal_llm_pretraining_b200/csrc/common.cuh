@@ -86,28 +86,29 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // erfc(z), z >= 0, by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 1 MUFU.RCP, 1 MUFU.EX2 and
 // 7 FMAs instead of libdevice erff's ~40-instruction dependent chain — the GEMM epilogue is latency-bound on this.
 // The negative tail uses 1 + erf(z) = erfc(-z) directly, so there is no cancellation for x << 0.
-__device__ __forceinline__ void gelu_terms(float x, float& two_cdf, float& e) {
-    const float z = fabsf(x) * 0.70710678118654752f;
+// half_erfc = 0.5 * erfc(|x| / sqrt2) = 1 - Phi(|x|); e = exp(-x^2 / 2). 9 FP32 + 2 MUFU instructions.
+__device__ __forceinline__ void gelu_terms(float x, float& half_erfc, float& e) {
+    const float u = fabsf(x);
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(u, 0.3275911f * 0.70710678118654752f, 1.0f)));
+    float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
     poly *= t;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));  // exp(-x^2/2)
-    const float q = poly * e;  // erfc(|x|/sqrt2)
-    two_cdf = x >= 0.f ? 2.0f - q : q;  // 2 * Phi(x)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((u * -0.72134752044448170f) * u));  // exp(-x^2/2)
+    half_erfc = poly * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-    float c2, e;
-    gelu_terms(x, c2, e);
-    return 0.5f * x * c2;
+    float q, e;
+    gelu_terms(x, q, e);
+    return fmaf(-fabsf(x), q, fmaxf(x, 0.f));  // x >= 0: x (1 - q);  x < 0: x q  (no cancellation in the negative tail)
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    float c2, e;
-    gelu_terms(x, c2, e);
-    return fmaf(x * e, 0.39894228040143268f, 0.5f * c2);  // Phi(x) + x * phi(x)
+    float q, e;
+    gelu_terms(x, q, e);
+    const float cdf = x >= 0.f ? 1.0f - q : q;
+    return fmaf(x * e, 0.39894228040143268f, cdf);  // Phi(x) + x * phi(x)
 }
 
 // ------------------------------------------------------------------------------------------------

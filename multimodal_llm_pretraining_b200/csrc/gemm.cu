@@ -84,24 +84,26 @@ constexpr size_t gemm_smem_bytes() {
 // EPI (compile time, keeps the instruction footprint of the hot loop small — a fully generic, fully unrolled epilogue
 // was 350 KB of SASS and instruction-fetch bound): 0 = bias/residual/alpha/accumulate, 1 = + exact-erf GELU (+ aux
 // pre-activation output), 2 = + multiply by gelu'(dgelu_in).
-template <int EPI>
+template <int EPI, int SIDE>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], const uint4 (&side)[4],
                                                const float* sbias, int row, int col0, float alpha, uint8_t* stage_main,
                                                uint8_t* stage_aux, int half, int r) {
     if (!p.tma_store && row >= p.M) return;
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
-#pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
         const int col = col0 + g8 * 8;
         if (col >= p.N) break;  // N % 8 == 0
         float* x = &f[g8 * 8];
-        if (p.bias) {
+        if (p.bias) {  // acc * alpha + bias in one FFMA per element
             const float4 b0 = *reinterpret_cast<const float4*>(sbias + g8 * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(sbias + g8 * 8 + 4);
-            x[0] += b0.x, x[1] += b0.y, x[2] += b0.z, x[3] += b0.w;
-            x[4] += b1.x, x[5] += b1.y, x[6] += b1.z, x[7] += b1.w;
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaf(__uint_as_float(v[g8 * 8 + j]), alpha, bb[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]) * alpha;
         }
         if (EPI == 1 && p.aux_out) {
             const uint4 av = make_uint4(f2_to_bf2(x[0], x[1]), f2_to_bf2(x[2], x[3]), f2_to_bf2(x[4], x[5]), f2_to_bf2(x[6], x[7]));
@@ -112,8 +114,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
         }
+        // SIDE = 1: the residual / dgelu_in tile was TMA-loaded into the output slab itself and is replaced in place
+        const uint4 side_v = SIDE ? ld_shared_v4(stage_main + sw128_offset(r, half * 4 + g8)) : side[g8];
         if (EPI == 2) {
-            const uint4 hv = side[g8];
+            const uint4 hv = side_v;
             const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -123,7 +127,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             }
         }
         if (p.residual) {
-            const uint4 rv = side[g8];
+            const uint4 rv = side_v;
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -169,17 +173,19 @@ struct GemmGeom {
 };
 
 // smem per CTA: ring of STAGES x (A 16 KB + B (BN/CG) x 128 B) + two 16 KB output slabs + barriers + bias [2][BN]
-template <int EPI>
+template <int EPI, int SIDE>
 constexpr uint32_t gemm_stage_bytes() {
-    return EPI == 1 ? 65536u : 32768u;  // per epilogue group: one 16 KB output slab (+ one for the pre-GELU aux output)
+    // per epilogue group: one 16 KB output slab, plus one for the pre-GELU aux output (EPI 1) or to double-buffer the
+    // TMA-loaded residual / dgelu_in tiles (SIDE)
+    return (EPI == 1 || SIDE) ? 65536u : 32768u;
 }
-template <int BN, int STAGES, int CG, int EPI>
+template <int BN, int STAGES, int CG, int EPI, int SIDE>
 constexpr size_t gemm_smem_bytes_cg() {
-    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<EPI>();
+    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<EPI, SIDE>();
     return need + 1024 <= 232448 ? need + 1024 : 232448;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG, int SIDE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
@@ -197,18 +203,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
     constexpr uint32_t RING_BYTES = STAGES * (A_BYTES + B_BYTES);
-    constexpr uint32_t STG = gemm_stage_bytes<EPI>();
+    constexpr uint32_t STG = gemm_stage_bytes<EPI, SIDE>();
+    static_assert(!(SIDE && EPI == 1), "the GELU variant has no side operand");
     uint8_t* sstage = smem + RING_BYTES;  // output slabs (1024-aligned: the ring is a multiple of 16 KB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + STG);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = bars + 2 * STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* side_full = bars + 2 * STAGES + 4;  // [2 groups][2 buffers] (SIDE only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
     float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + STG + 256);  // [2][BN]
     static_assert(RING_BYTES % 1024 == 0, "staging slabs must be 1024B aligned");
-    static_assert((2 * STAGES + 5) * 8 <= 256, "barrier block overflow");
-    if (threadIdx.x == 0 && (smem + RING_BYTES + STG + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes_cg<BN, STAGES, CG, EPI>())) {
+    static_assert((2 * STAGES + 9) * 8 <= 256, "barrier block overflow");
+    if (threadIdx.x == 0 && (smem + RING_BYTES + STG + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes_cg<BN, STAGES, CG, EPI, SIDE>())) {
         printf("b200pt gemm: dynamic smem base misaligned beyond slack\n");
         __trap();
     }
@@ -233,6 +241,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 8 * CG);  // every epilogue warp of every CTA of the pair
         }
+        for (int s = 0; s < 4; ++s) mbar_init(&side_full[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -356,11 +365,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int et = et_all & 127;          // 0..127 inside the group
         const int bar_id = 1 + grp;
         const float alpha = (p.alpha_dev ? __ldg(p.alpha_dev) : 1.0f) * p.alpha_host;
-        const __nv_bfloat16* side_ptr = p.residual ? p.residual : p.dgelu_in;
         constexpr int NC = BN / 32;
         uint8_t* st_main = sstage + grp * (STG / 2);
-        uint8_t* st_aux = st_main + 16384;  // EPI == 1 only
-        const bool has_side = side_ptr != nullptr;
+        uint8_t* st_aux = st_main + 16384;  // EPI == 1: pre-GELU slab; SIDE: second buffer of the in-place ring
+        const int r_in_tile = quarter * 32 + lane;
+        // ---- SIDE: this group's slabs form one sequence j = 0,1,2,... over all its tiles; slab j lives in buffer j & 1. The
+        // residual / dgelu_in tile of slab j+1 is TMA-loaded while slab j is processed, so its latency is never exposed and
+        // the loads are full 128-byte lines (per-thread global loads of a row-major tile touch 32 lines per instruction).
+        auto slab_valid = [&](int tile, int k) {
+            int z, tm, tn, kb0, kb1;
+            decode(tile, z, tm, tn, kb0, kb1);
+            return tn * BN + (grp + 2 * k) * 64 < p.N;
+        };
+        auto next_slab = [&](int& tile, int& k) {  // successor of (tile, k) in this group's sequence; tile >= num_tiles at the end
+            do {
+                if (k == 0) k = 1;
+                else k = 0, tile += n_workers;
+            } while (tile < num_tiles && !slab_valid(tile, k));
+        };
+        auto issue_side = [&](int tile, int k, int buf) {  // one elected thread
+            int z, tm, tn, kb0, kb1;
+            decode(tile, z, tm, tn, kb0, kb1);
+            uint64_t* bar = &side_full[grp * 2 + buf];
+            mbar_expect_tx(bar, 16384);
+            tma_load_2d(st_main + buf * 16384, &tmAux, bar, tn * BN + (grp + 2 * k) * 64, tm * TILE_M + static_cast<int>(rank) * GEMM_BM);
+        };
+        int sj = 0;  // running slab count of this group
+        if (SIDE) {
+            int t0 = worker, k0 = 0;
+            if (t0 < num_tiles && !slab_valid(t0, k0)) next_slab(t0, k0);
+            if (et == 0 && t0 < num_tiles) issue_side(t0, k0, 0);
+        }
         int as = 0;
         uint32_t aph = 0;
         for (int tile = worker; tile < num_tiles; tile += n_workers) {
@@ -378,60 +413,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int i = et_all; i < BN; i += 256) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
                 asm volatile("bar.sync 3, 256;" ::: "memory");
             }
-            auto load_side = [&](int c, uint4 (&r)[4]) {
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    const int col = n0 + c * 32 + g8 * 8;
-                    r[g8] = (has_side && row < p.M && col < p.N)
-                                ? ld_nc_v4(side_ptr + static_cast<size_t>(row) * p.ldr + col)
-                                : make_uint4(0, 0, 0, 0);
-                }
-            };
             const int rem = p.N - n0;
             const int nc_valid = rem >= BN ? NC : (rem + 31) / 32;  // chunks that hold at least one valid column
-            const int r_in_tile = quarter * 32 + lane;
-            // The residual / dgelu_in slices do not depend on the accumulator: fetch the first slab's before waiting for
-            // the MMAs and every later slab's one iteration ahead, so their HBM latency never sits on the critical path.
-            uint4 side0[4], side1[4];
-            if (has_side) {
-                load_side(2 * grp, side0);
-                load_side(2 * grp + 1, side1);
-            }
             mbar_wait(&tfull[as], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            const uint4 no_side[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
 #pragma unroll 1
             for (int c0 = 2 * grp; c0 < nc_valid; c0 += 4) {  // rolled: one slab (two chunk bodies) of code
                 const bool two = c0 + 1 < nc_valid;
                 uint32_t v0[32], v1[32];
-                uint4 nside0[4], nside1[4];
                 tmem_ld_32x32(t_addr + c0 * 32, v0);
                 if (two) tmem_ld_32x32(t_addr + (c0 + 1) * 32, v1);
-                if (has_side && c0 + 4 < nc_valid) {
-                    load_side(c0 + 4, nside0);
-                    load_side(c0 + 5, nside1);
-                }
-                if (p.tma_store) {
+                uint8_t* slab = st_main;
+                if (SIDE) {
+                    const int buf = sj & 1;
+                    slab = st_main + buf * 16384;
+                    if (et == 0) {
+                        // the other buffer was last read by the TMA store of slab sj-1: once that has drained, refill it
+                        tma_store_wait_read<0>();
+                        int nt = tile, nk = (c0 - 2 * grp) >> 2;
+                        next_slab(nt, nk);
+                        if (nt < num_tiles) issue_side(nt, nk, buf ^ 1);
+                    }
+                    mbar_wait(&side_full[grp * 2 + buf], (sj >> 1) & 1);
+                    ++sj;
+                } else if (p.tma_store) {
                     // this group's slab buffer must have been drained by the TMA store that last read it
                     if (et == 0) tma_store_wait_read<0>();
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 }
                 tmem_ld_wait();
                 if (p.debug & 1) continue;
-                epilogue_chunk<EPI>(p, v0, side0, sb + c0 * 32, row, n0 + c0 * 32, alpha, st_main, st_aux, 0, r_in_tile);
-                if (two) epilogue_chunk<EPI>(p, v1, side1, sb + (c0 + 1) * 32, row, n0 + (c0 + 1) * 32, alpha, st_main, st_aux, 1, r_in_tile);
+                epilogue_chunk<EPI, SIDE>(p, v0, no_side, sb + c0 * 32, row, n0 + c0 * 32, alpha, slab, st_aux, 0, r_in_tile);
+                if (two) epilogue_chunk<EPI, SIDE>(p, v1, no_side, sb + (c0 + 1) * 32, row, n0 + (c0 + 1) * 32, alpha, slab, st_aux, 1, r_in_tile);
                 if (p.tma_store) {
                     fence_proxy_async_smem();
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (et == 0) {
-                        tma_store_2d(&tmC, st_main, c_n0 + (c0 >> 1) * 64, c_m0);
+                        tma_store_2d(&tmC, slab, c_n0 + (c0 >> 1) * 64, c_m0);
                         if (EPI == 1 && p.aux_out) tma_store_2d(&tmAux, st_aux, c_n0 + (c0 >> 1) * 64, c_m0);
                         tma_store_commit();
                     }
-                }
-                if (has_side) {
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) side0[g8] = nside0[g8], side1[g8] = nside1[g8];
                 }
             }
             tc_fence_before();
@@ -504,15 +527,15 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
 template <int BN, int STAGES, int CG>
 constexpr int gelu_stages() {
     int st = STAGES;
-    while (static_cast<size_t>(st) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<1>() + 1024 > 232448) --st;
+    while (static_cast<size_t>(st) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<1, 0>() + 1024 > 232448) --st;
     return st;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int CG, int SIDE = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t st) {
-    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, CG>;
-    constexpr size_t smem = gemm_smem_bytes_cg<BN, STAGES, CG, EPI>();
+    auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, CG, SIDE>;
+    constexpr size_t smem = gemm_smem_bytes_cg<BN, STAGES, CG, EPI, SIDE>();
     static bool configured = false;  // benign race: attribute set is idempotent
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -571,9 +594,19 @@ static int dispatch_major(const b200_gemm_args* a, GemmParams& p, cudaStream_t s
         if (a->a_mn || a->b_mn) return fail(-1, "gemm: the GELU epilogue is built for the forward layout (a_mn=0, b_mn=0) only");
         return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, false, 1, CG>(tmA, tmB, tmC, tmAux, p, st);
     }
+    // residual / dgelu_in ("side" operands) are TMA-loaded into the output slabs: bf16 TMA-stored outputs only
+    const void* side = a->residual ? a->residual : a->dgelu_in;
+    if (side) {
+        if (!p.tma_store) return fail(-1, "gemm: residual / dgelu_in need a bf16, non-accumulating output");
+        if ((rc = make_tmap_bf16_2d(&tmAux, side, a->N, a->M, a->ldr, 64, GEMM_BM))) return rc;
+    }
     if (a->dgelu_in) {
         if (a->a_mn || !a->b_mn) return fail(-1, "gemm: the dGELU epilogue is built for the dgrad layout (a_mn=0, b_mn=1) only");
-        return launch_gemm<BN, STAGES, false, true, 2, CG>(tmA, tmB, tmC, tmAux, p, st);
+        return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, true, 2, CG, 1>(tmA, tmB, tmC, tmAux, p, st);
+    }
+    if (a->residual) {
+        if (a->a_mn || a->b_mn) return fail(-1, "gemm: the residual epilogue is built for the forward layout (a_mn=0, b_mn=0) only");
+        return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, false, 0, CG, 1>(tmA, tmB, tmC, tmAux, p, st);
     }
     if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
     if (!a->a_mn && a->b_mn) return launch_gemm<BN, STAGES, false, true, 0, CG>(tmA, tmB, tmC, tmAux, p, st);
