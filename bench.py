@@ -36,8 +36,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="pythia-1b")
-    ap.add_argument("--mbs", type=int, default=16)
+    ap.add_argument("--mbs", type=int, default=None, help="micro-batch size (default 16 for Pythia, 64 for RoBERTa)")
     ap.add_argument("--grad-acc", type=int, default=16)
+    ap.add_argument("--seq-len", type=int, default=None, help="RoBERTa only: 512 (default) or 128")
     ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1"])
     ap.add_argument("--checkpointing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -159,6 +160,8 @@ def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if a.mbs is None:
+        a.mbs = 16
     cb = run_cpu_baseline(a.model, a.cpu_sample_tokens, a.steps, a.warmup)
     line = {
         "impl": "reference", "metric": "train_tokens_per_s", "value": cb["value"], "unit": "tokens/s", "n_gpus": a.gpus,
@@ -181,7 +184,7 @@ def main_b200(a):
     from multimodal_llm_pretraining_b200 import kernels as K
     from multimodal_llm_pretraining_b200.engine import TrainEngine
     from multimodal_llm_pretraining_b200.models import get_model_class
-    from multimodal_llm_pretraining_b200.models.configs import neox_train_flops_per_sequence
+    from multimodal_llm_pretraining_b200.models.configs import neox_train_flops_per_sequence, roberta_train_flops_per_sequence
     from multimodal_llm_pretraining_b200.optim import get_scheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,10 +202,20 @@ def main_b200(a):
 
     mc = get_model_class(a.model)
     cfg = mc.config_dict()
-    S_in = mc.sequence_length  # 2049 tokens in, 2048 predicted
-    S_pred = S_in - 1
+    is_roberta = a.model == "roberta"
+    if a.mbs is None:
+        a.mbs = 64 if is_roberta else 16
+    if is_roberta:
+        S_in = S_pred = a.seq_len or mc.sequence_length  # masked LM: every position is predicted (labels = input_ids)
+    else:
+        S_in = mc.sequence_length  # 2049 tokens in, 2048 predicted
+        S_pred = S_in - 1
     torch.manual_seed(0)
-    model = mc.build_model(use_custom_kernels=True).to(dev).train()
+    model = mc.build_model(use_custom_kernels=True)
+    if is_roberta:
+        # attention-probability dropout has no kernel yet: the timing run says so in `config`
+        model.allow_missing_attention_dropout = True
+    model = model.to(dev).train()
     if a.checkpointing:
         model.gradient_checkpointing_enable()
     okw = dict(mc.optimizer_kwargs)
@@ -282,7 +295,7 @@ def main_b200(a):
     ms_per_step = ms_total / a.steps
     value = tokens_per_step / (ms_per_step / 1e3)
     e2e_value = tokens_per_step / (ms_e2e / a.steps / 1e3)
-    f_tok = neox_train_flops_per_sequence(cfg, S_in) / S_pred
+    f_tok = (roberta_train_flops_per_sequence(cfg, S_in) if is_roberta else neox_train_flops_per_sequence(cfg, S_in)) / S_pred
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -295,7 +308,7 @@ def main_b200(a):
 
     if rank == 0:
         cpu = None
-        if not a.no_cpu_baseline and world == 1:
+        if not a.no_cpu_baseline and world == 1 and not is_roberta:  # the CPU arm is the Pythia reference path
             cpu = run_cpu_baseline(a.model, a.cpu_sample_tokens, 1, 1)
         line = {
             "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
@@ -306,6 +319,7 @@ def main_b200(a):
                             f"+ clip + fused Adam (random-init weights, uniform random tokens)",
                 "model": a.model, "micro_batch": mbs, "grad_acc": ga, "global_batch_sequences": world * ga * mbs,
                 "seq_len": S_in, "parallelism": f"{strategy}x{world}", "activation_checkpointing": bool(a.checkpointing),
+                **({"note": "hidden dropout 0.1 applied; attention-probability dropout (0.1 in roberta-large) NOT applied: no kernel yet"} if is_roberta else {}),
                 "l2": "working set per step (>= 2 GB of weights, > 30 GB of activations) far exceeds the 126 MB L2; no explicit flush",
             },
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": ga * mbs * S_in * 8, "d2h_bytes_per_step": 4,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 5
+#define B200PT_ABI_VERSION 6
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
@@ -65,10 +65,24 @@ int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int T, 
                        b200_stream_t stream);
 int b200_embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int T, int h, int vocab,
                        b200_stream_t stream);
+/* Same, for nn.Embedding(padding_idx=...): tokens whose id == padding_idx contribute nothing (RoBERTa word and position
+ * tables, HF:models/roberta/modeling_roberta.py:61,74-76). */
+int b200_embedding_bwd_padding(const int64_t* ids, const void* dout, float* dtable, int T, int h, int64_t padding_idx,
+                               b200_stream_t stream);
 /* out[t,:] = LN-less sum of up to three bf16 table rows (RoBERTa word + position + token-type,
  * HF:models/roberta/modeling_roberta.py:56-144); ids1/ids2 may be NULL. */
 int b200_embedding3_fwd(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1,
                         const int64_t* ids2, const void* table2, void* out, int T, int h, b200_stream_t stream);
+
+/* RoBERTa position ids: pos = cumsum(ids != pad) * (ids != pad) + pad along each row
+ * (create_position_ids_from_input_ids, HF:models/roberta/modeling_roberta.py:146-159). int64 in / out [B, S]. */
+int b200_roberta_position_ids(const int64_t* ids, int64_t* pos, int B, int S, int64_t pad_id, b200_stream_t stream);
+
+/* ---------------------------------------------------------------- Dropout (nn.Dropout on the RoBERTa path,
+ * HF:models/roberta/modeling_roberta.py:65,339,397): out = x * mask / (1 - p) (+ residual), bf16, n elements (n % 8 == 0).
+ * The mask is a pure function of (seed, element index), so backward calls the same entry point on the gradient with the
+ * same seed (residual = NULL) instead of storing a mask. p is quantised to 1/65536. */
+int b200_dropout(const void* x, const void* residual, void* out, size_t n, float p, uint64_t seed, b200_stream_t stream);
 
 /* ---------------------------------------------------------------- Cross entropy over the vocabulary
  * Replaces ForCausalLMLoss / fixed_cross_entropy (HF:loss/loss_utils.py:28-67): fp32 log-softmax + NLL, mean over

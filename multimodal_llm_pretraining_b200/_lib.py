@@ -14,7 +14,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200pt.so"
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -70,7 +70,10 @@ SIGNATURES = {
     "b200_rope_qk_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_embedding_bwd_padding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "b200_embedding3_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_void_p]),
+    "b200_roberta_position_ids": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    "b200_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, C.c_uint64, c_void_p]),
     "b200_count_valid": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "b200_cross_entropy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
     "b200_mean_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -161,11 +161,13 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __re
 // scatter-add into fp32 table gradient. Random ids over a 50k vocab rarely collide, so plain fp32 REDs are cheap.
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dout, float* __restrict__ dtable,
-                     int T, int h) {
+                     int T, int h, int64_t skip_id) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
-        float* drow = dtable + static_cast<size_t>(ids[t]) * h;
+        const int64_t id = ids[t];
+        if (id == skip_id) continue;  // nn.Embedding(padding_idx=...): the padding row receives no gradient
+        float* drow = dtable + static_cast<size_t>(id) * h;
         const __nv_bfloat16* g = dout + static_cast<size_t>(t) * h;
         for (int c = lane * 8; c < h; c += 256) {
             const uint4 v = ld_nc_v4(g + c);
@@ -250,6 +252,70 @@ colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int col
     out[c] += t;
 }
 
+
+// ----------------------------------------------------------------------------------------------- RoBERTa position ids
+// pos[b, s] = (number of non-pad tokens in ids[b, 0..s]) * (ids[b, s] != pad) + pad   (HF:modeling_roberta.py:146-159).
+// One warp per row: inclusive warp scan over 32-token chunks with a running carry. Integer-exact.
+__global__ void __launch_bounds__(128)
+position_ids_kernel(const int64_t* __restrict__ ids, int64_t* __restrict__ pos, int B, int S, int64_t pad) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const int64_t* r = ids + static_cast<size_t>(row) * S;
+    int64_t* o = pos + static_cast<size_t>(row) * S;
+    int carry = 0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        const int m = (s < S && r[s] != pad) ? 1 : 0;
+        int inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (s < S) o[s] = static_cast<int64_t>((carry + inc) * m) + pad;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- dropout
+// Counter-based: element i keeps iff the 16-bit lane (i & 3) of mix64(seed, i >> 2) >= thr16, with thr16 = round(p * 65536);
+// kept values are scaled by 65536 / (65536 - thr16) so that E[out] = in exactly. The mask is a pure function of
+// (seed, element index): the backward pass recomputes it instead of storing it.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+// out = dropout(x) (+ residual); 8 elements per thread per step
+__global__ void __launch_bounds__(256)
+dropout_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual, uint4* __restrict__ out, size_t n_vec,
+               uint32_t thr16, float keep_scale, uint64_t seed) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint4 v = ld_nc_v4(x + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t rw[4] = {0, 0, 0, 0};
+        if (residual != nullptr) {
+            const uint4 r = ld_nc_v4(residual + i);
+            rw[0] = r.x, rw[1] = r.y, rw[2] = r.z, rw[3] = r.w;
+        }
+        const uint64_t h0 = mix64(seed + 0x9e3779b97f4a7c15ull * (2 * i + 1)), h1 = mix64(seed + 0x9e3779b97f4a7c15ull * (2 * i + 2));
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t hh = j < 2 ? h0 : h1;
+            const uint32_t ra = static_cast<uint32_t>(hh >> (32 * (j & 1))) & 0xffffu, rb = static_cast<uint32_t>(hh >> (32 * (j & 1) + 16)) & 0xffffu;
+            const float2 f = bf2_to_f2(w[j]);
+            const float2 r = bf2_to_f2(rw[j]);
+            o[j] = f2_to_bf2((ra >= thr16 ? f.x * keep_scale : 0.f) + r.x, (rb >= thr16 ? f.y * keep_scale : 0.f) + r.y);
+        }
+        st_v4(out + i, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
 }  // namespace b200
 
 using namespace b200;
@@ -303,8 +369,15 @@ extern "C" int b200_embedding_bwd(const int64_t* ids, const void* dout, float* d
     (void)vocab;
     B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h);
+    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, -1);
     return check_launch("embedding_bwd");
+}
+extern "C" int b200_embedding_bwd_padding(const int64_t* ids, const void* dout, float* dtable, int T, int h, int64_t padding_idx,
+                                          b200_stream_t stream) {
+    B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
+    const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
+    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, padding_idx);
+    return check_launch("embedding_bwd_padding");
 }
 
 extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200_stream_t stream) {
@@ -337,4 +410,21 @@ extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, f
     if (rc) return rc;
     colsum_finalize_kernel<<<(cols + 255) / 256, 256, 0, as_stream(stream)>>>(part, chunks, cols, out);
     return check_launch("colsum_finalize");
+}
+
+extern "C" int b200_roberta_position_ids(const int64_t* ids, int64_t* pos, int B, int S, int64_t pad_id, b200_stream_t stream) {
+    B200_REQUIRE(B > 0 && S > 0, "position_ids: bad shape");
+    position_ids_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(ids, pos, B, S, pad_id);
+    return check_launch("roberta_position_ids");
+}
+
+extern "C" int b200_dropout(const void* x, const void* residual, void* out, size_t n, float p, uint64_t seed, b200_stream_t stream) {
+    B200_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(out) && (!residual || aligned16(residual)), "dropout: n %% 8 == 0 and 16B-aligned pointers");
+    B200_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+    const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    const float keep = 65536.0f / static_cast<float>(65536u - thr);
+    const size_t n_vec = n / 8;
+    dropout_kernel<<<ew_grid(n_vec, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(residual),
+                                                                        static_cast<uint4*>(out), n_vec, thr, keep, seed);
+    return check_launch("dropout");
 }

@@ -605,7 +605,8 @@ static int dispatch_major(const b200_gemm_args* a, GemmParams& p, cudaStream_t s
         return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, true, 2, CG, 1>(tmA, tmB, tmC, tmAux, p, st);
     }
     if (a->residual) {
-        if (a->a_mn || a->b_mn) return fail(-1, "gemm: the residual epilogue is built for the forward layout (a_mn=0, b_mn=0) only");
+        if (a->a_mn) return fail(-1, "gemm: the residual epilogue is built for the forward and dgrad layouts (a_mn=0) only");
+        if (a->b_mn) return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, true, 0, CG, 1>(tmA, tmB, tmC, tmAux, p, st);
         return launch_gemm<BN, gelu_stages<BN, STAGES, CG>(), false, false, 0, CG, 1>(tmA, tmB, tmC, tmAux, p, st);
     }
     if (!a->a_mn && !a->b_mn) return launch_gemm<BN, STAGES, false, false, 0, CG>(tmA, tmB, tmC, tmAux, p, st);

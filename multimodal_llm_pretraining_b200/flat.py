@@ -20,14 +20,18 @@ ALIGN = 64
 
 
 class FlatParams:
-    def __init__(self, shapes: list[tuple[str, tuple[int, ...]]], device="cpu"):
-        self.names = [n for n, _ in shapes]
-        self.shapes = {n: tuple(s) for n, s in shapes}
+    def __init__(self, shapes: list[tuple], device="cpu"):
+        """shapes: (name, shape) or (name, shape, alloc_shape): alloc_shape >= shape reserves zero padding behind the
+        parameter (e.g. RoBERTa's 50265-row vocabulary padded to 50304 rows so that the tied decoder GEMM, its wgrad and
+        the cross entropy run on 16-byte-aligned rows); the nn.Parameter and state_dict see `shape` only."""
+        self.names = [e[0] for e in shapes]
+        self.shapes = {e[0]: tuple(e[1]) for e in shapes}
+        self.alloc_shapes = {e[0]: tuple(e[2]) if len(e) > 2 else tuple(e[1]) for e in shapes}
         self.offsets: dict[str, int] = {}
         off = 0
-        for n, s in shapes:
+        for n in self.names:
             self.offsets[n] = off
-            off += (math.prod(s) + ALIGN - 1) // ALIGN * ALIGN
+            off += (math.prod(self.alloc_shapes[n]) + ALIGN - 1) // ALIGN * ALIGN
         # total padded to a multiple of 8 * ALIGN so it splits evenly into up to 8 aligned ZeRO shards
         self.numel = (off + 8 * ALIGN - 1) // (8 * ALIGN) * (8 * ALIGN)
         self.master = torch.zeros(self.numel, dtype=torch.float32, device=device)
@@ -42,10 +46,21 @@ class FlatParams:
         o, s = self.offsets[name], self.shapes[name]
         return buf[o:o + math.prod(s)].view(s)
 
+    def view_alloc(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        """View including the zero padding reserved behind the parameter (alloc_shape)."""
+        o, s = self.offsets[name], self.alloc_shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def view_span(self, buf: torch.Tensor, first: str, shape: tuple[int, ...]) -> torch.Tensor:
+        """View of `shape` starting at parameter `first` and running over the parameters laid out behind it (e.g. RoBERTa's
+        query/key/value weights, contiguous in the store, as one [3h, h] matrix)."""
+        o = self.offsets[first]
+        return buf[o:o + math.prod(shape)].view(shape)
+
     def range_of(self, names: list[str]) -> tuple[int, int]:
         """[start, end) element range covering the (contiguous) parameters `names`, including alignment padding."""
         starts = [self.offsets[n] for n in names]
-        ends = [self.offsets[n] + (math.prod(self.shapes[n]) + ALIGN - 1) // ALIGN * ALIGN for n in names]
+        ends = [self.offsets[n] + (math.prod(self.alloc_shapes[n]) + ALIGN - 1) // ALIGN * ALIGN for n in names]
         return min(starts), max(ends)
 
     def make_parameter(self, name: str) -> nn.Parameter:

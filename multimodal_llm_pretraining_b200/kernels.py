@@ -128,11 +128,34 @@ def embedding3_fwd(ids0, table0, ids1=None, table1=None, ids2=None, table2=None)
     return out
 
 
-def embedding_bwd(ids, dout, dtable):
+def embedding_bwd(ids, dout, dtable, padding_idx=None):
+    """dtable[ids[t]] += dout[t] (fp32 atomics); rows with ids == padding_idx are skipped (nn.Embedding padding_idx)."""
     _req(dout.dtype == BF16 and dout.is_contiguous() and dtable.dtype == F32, "embedding_bwd: dout bf16, dtable fp32")
     T, h = ids.numel(), dtable.shape[1]
-    check(_L(dout).b200_embedding_bwd(ptr(ids), ptr(dout), ptr(dtable), T, h, dtable.shape[0], stream_ptr()), "b200_embedding_bwd")
+    if padding_idx is None:
+        check(_L(dout).b200_embedding_bwd(ptr(ids), ptr(dout), ptr(dtable), T, h, dtable.shape[0], stream_ptr()), "b200_embedding_bwd")
+    else:
+        check(_L(dout).b200_embedding_bwd_padding(ptr(ids), ptr(dout), ptr(dtable), T, h, int(padding_idx), stream_ptr()), "b200_embedding_bwd_padding")
     _count(1)
+
+
+def roberta_position_ids(ids, pad_id: int):
+    """int64 [B,S] -> int64 [B,S]: cumsum(ids != pad) * (ids != pad) + pad (HF create_position_ids_from_input_ids)."""
+    _req(ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous(), "position_ids: ids must be contiguous int64 [B,S]")
+    pos = torch.empty_like(ids)
+    check(_L(ids).b200_roberta_position_ids(ptr(ids), ptr(pos), ids.shape[0], ids.shape[1], int(pad_id), stream_ptr()), "b200_roberta_position_ids")
+    _count(1)
+    return pos
+
+
+def dropout(x, p: float, seed: int, residual=None, out=None):
+    """out = dropout(x) (+ residual), mask = f(seed, element index); call again on the gradient with the same seed for backward."""
+    _req(x.dtype == BF16 and x.is_contiguous() and x.numel() % 8 == 0, "dropout: contiguous bf16 with numel % 8 == 0")
+    _req(residual is None or (residual.dtype == BF16 and residual.is_contiguous() and residual.numel() == x.numel()), "dropout: bad residual")
+    out = torch.empty_like(x) if out is None else out
+    check(_L(x).b200_dropout(ptr(x), ptr(residual), ptr(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "b200_dropout")
+    _count(1)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------- Cross entropy

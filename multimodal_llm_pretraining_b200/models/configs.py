@@ -67,3 +67,14 @@ def neox_train_flops_per_sequence(d: dict, S: int) -> int:
     """F(S) = 6 S W_lin + 12 L h S^2 — equals torch FlopCounterMode on fwd+bwd, the reference's FLOP definition
     (src/benchmarking/flops.py:28-36)."""
     return 6 * S * neox_linear_weight_count(d) + 12 * d["num_hidden_layers"] * d["hidden_size"] * S * S
+
+
+def roberta_linear_weight_count(d: dict) -> int:
+    """W_lin for RoBERTa: encoder Linear weights + lm_head.dense + the tied decoder (counted once as a GEMM)."""
+    h, V, L, I = d["hidden_size"], d["vocab_size"], d["num_hidden_layers"], d["intermediate_size"]
+    return L * (4 * h * h + 2 * I * h) + h * h + V * h
+
+
+def roberta_train_flops_per_sequence(d: dict, S: int) -> int:
+    """F(S) = 6 S W_lin + 12 L h S^2 (bidirectional attention: no causal discount applies)."""
+    return 6 * S * roberta_linear_weight_count(d) + 12 * d["num_hidden_layers"] * d["hidden_size"] * S * S

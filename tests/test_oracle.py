@@ -80,3 +80,27 @@ def test_schedule_matches_hf_formula():
     for s in (0, 10, 1429, 1430, 50000, 143000):
         assert abs(cosine_with_min_lr_lambda(s, num_warmup_steps=1430, num_training_steps=143000, min_lr_rate=0.1)
                    - O.cosine_with_min_lr(s, 1430, 143000, 0.1)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------- RoBERTa oracle
+@pytest.fixture(scope="module")
+def rgold():
+    return torch.load(Path(__file__).resolve().parent / "golden" / "roberta_tiny.pt", weights_only=False)
+
+
+def test_roberta_oracle_matches_hf_golden(rgold):
+    from oracle import roberta_oracle as R
+
+    ids = rgold["batches"][0]
+    loss, grads, logits = R.roberta_loss_and_grads(rgold["state_dict"], ids, ids, rgold["cfg"])
+    assert torch.allclose(logits, rgold["logits0"], atol=2e-5, rtol=1e-5)
+    assert abs(loss.item() - rgold["loss0"].item()) <= 1e-5
+    for k, g in rgold["grads0"].items():
+        assert torch.allclose(grads[k], g, atol=1e-6, rtol=1e-4), k
+
+
+def test_roberta_position_ids_rule(rgold):
+    from oracle import roberta_oracle as R
+
+    ids = torch.tensor([[0, 5, 1, 7, 1, 1, 9], [1, 1, 4, 4, 4, 1, 2]])
+    assert R.position_ids(ids, 1).tolist() == [[2, 3, 1, 4, 1, 1, 5], [1, 1, 2, 3, 4, 1, 5]]

@@ -41,6 +41,35 @@ def test_flat_module_param_count_and_hf_keys():
     assert torch.all(m.state_dict()["gpt_neox.layers.0.input_layernorm.weight"] == 1)
 
 
+def test_roberta_module_param_count_keys_and_flops():
+    from multimodal_llm_pretraining_b200.modeling_roberta import B200RobertaForMaskedLM
+
+    cfg = C.roberta_large_config_dict()
+    small = dict(cfg, num_hidden_layers=2)
+    m = B200RobertaForMaskedLM(C.as_namespace(small))
+    tr = pytest.importorskip("transformers")
+    with torch.device("meta"):
+        hf = tr.RobertaForMaskedLM(tr.RobertaConfig(**small))
+    assert sorted(m.state_dict()) == sorted(hf.state_dict())
+    for k, v in hf.state_dict().items():
+        assert m.state_dict()[k].shape == v.shape, k
+    assert sum(p.numel() for p in m.parameters()) == sum(p.numel() for p in hf.parameters())
+    # full roberta-large count (published) without building it: closed form from the shapes
+    from multimodal_llm_pretraining_b200.modeling_roberta import roberta_param_shapes
+    import math
+
+    assert sum(math.prod(e[1]) for e in roberta_param_shapes(C.as_namespace(cfg))) == C.ROBERTA_LARGE_PARAM_COUNT
+    # q/k/v weights and biases are contiguous in the flat store (one fused [3h, h] GEMM operand)
+    f, h = m.flat, small["hidden_size"]
+    p0 = "roberta.encoder.layer.0.attention.self"
+    assert f.offsets[f"{p0}.key.weight"] - f.offsets[f"{p0}.query.weight"] == h * h
+    assert f.offsets[f"{p0}.value.bias"] - f.offsets[f"{p0}.query.bias"] == 2 * h
+    # W_lin and FLOPs per token of SURVEY.md section 8d
+    assert C.roberta_linear_weight_count(cfg) == 303_038_464 + 51_471_360
+    assert abs(C.roberta_train_flops_per_sequence(cfg, 512) / 512 / 1e9 - 2.278) < 2e-3
+    assert abs(C.roberta_train_flops_per_sequence(cfg, 128) / 128 / 1e9 - 2.165) < 2e-3
+
+
 def test_readme_training_arguments_golden():
     """scripts/to_training_arguments.py output for pythia-1b / free-lunch / zero_1 / mbs 16 / ga 16 (reference README.md:60-124)."""
     gold = json.load(open(ROOT / "tests" / "golden" / "readme_training_arguments.json"))
