@@ -25,6 +25,8 @@ namespace b200 {
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                       uint32_t box_inner, uint32_t box_outer);  // gemm.cu
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_elems,
+                      uint64_t pitch2_elems, uint32_t box0, uint32_t box2);  // gemm.cu
 
 constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr float LN2_F = 0.6931471805599453f;
@@ -59,8 +61,17 @@ struct AttnParams {
     int64_t dqkv_row_stride, dqkv_head_stride;
     __nv_bfloat16* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
     int trace;
+    int d_real;  // head_dim as stored (80 for Pythia-2.8b); the kernels run on D = d_real rounded up to 64/128/256 with the
+    int pad3d;   // tail columns zero-filled by 3-D TMA maps {d, head, token} (pad3d = 1) and clipped again on store
     __nv_bfloat16* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
 };
+
+// 64-column box c of head h, rows [row, row + box_rows): 2-D map {row width, tokens} or, for padded head dims, 3-D map
+// {d, head, token} whose out-of-extent columns arrive as zeros
+__device__ __forceinline__ void tma_load_head(void* dst, const CUtensorMap* m, uint64_t* bar, int col0, int c, int h, int row, int pad3d) {
+    if (pad3d) tma_load_3d(dst, m, bar, c * 64, h, row);
+    else tma_load_2d(dst, m, bar, col0 + c * 64, row);
+}
 
 // write 8 consecutive bf16 (one 16-byte chunk, index cc along the row) of row r into a [128 x 64*nsub] K-major
 // SWIZZLE_128B operand made of 16 KB sub-tiles (one per 64 columns)
@@ -148,16 +159,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // ---------------------------------------------------------------- TMA producer (one elected thread)
         if (elect_one()) {
             mbar_expect_tx(q_full, L::Q_BYTES);
-            for (int c = 0; c < NSUB; ++c) tma_load_2d(sQ + c * 16384, &tmQ, q_full, col0 + c * 64, row_base + q0);
+            for (int c = 0; c < NSUB; ++c) tma_load_head(sQ + c * 16384, &tmQ, q_full, col0, c, h, row_base + q0, p.pad3d);
             for (int j = 0; j < n_blocks; ++j) {
                 const int s = j % STAGES;
                 mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&k_full[s], L::KV_BYTES);
                 for (int c = 0; c < NSUB; ++c)
-                    tma_load_2d(sK + s * L::KV_BYTES + c * (BN * 128), &tmK, &k_full[s], col0 + c * 64, row_base + j * BN);
+                    tma_load_head(sK + s * L::KV_BYTES + c * (BN * 128), &tmK, &k_full[s], col0, c, h, row_base + j * BN, p.pad3d);
                 mbar_expect_tx(&v_full[s], L::KV_BYTES);
                 for (int c = 0; c < NSUB; ++c)
-                    tma_load_2d(sV + s * L::KV_BYTES + c * (BN * 128), &tmV, &v_full[s], col0 + c * 64, row_base + j * BN);
+                    tma_load_head(sV + s * L::KV_BYTES + c * (BN * 128), &tmV, &v_full[s], col0, c, h, row_base + j * BN, p.pad3d);
             }
         }
         __syncwarp();
@@ -295,7 +306,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
                     o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
                     o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
-                    st_v4(orow + c * 32 + g * 8, o);
+                    if (c * 32 + g * 8 < p.d_real) st_v4(orow + c * 32 + g * 8, o);
                 }
             }
         }
@@ -436,8 +447,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         if (elect_one()) {
             mbar_expect_tx(r_full, 2 * L::R_BYTES);
             for (int c = 0; c < NSUB; ++c) {
-                tma_load_2d(sR1 + c * 16384, &tmR1, r_full, col0 + c * 64, row_base + r0);
-                tma_load_2d(sR2 + c * 16384, &tmR2, r_full, (DKV ? col0 : col0_do) + c * 64, row_base + r0);
+                tma_load_head(sR1 + c * 16384, &tmR1, r_full, col0, c, h, row_base + r0, p.pad3d);
+                tma_load_head(sR2 + c * 16384, &tmR2, r_full, DKV ? col0 : col0_do, c, h, row_base + r0, p.pad3d);
             }
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % STAGES;
@@ -445,8 +456,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 mbar_expect_tx(&t_full[s], 2 * L::T_BYTES);
                 const int row = row_base + (t_begin + t) * BT;
                 for (int c = 0; c < NSUB; ++c) {
-                    tma_load_2d(sT1 + s * L::T_BYTES + c * 8192, &tmT1, &t_full[s], col0 + c * 64, row);
-                    tma_load_2d(sT2 + s * L::T_BYTES + c * 8192, &tmT2, &t_full[s], (DKV ? col0_do : col0) + c * 64, row);
+                    tma_load_head(sT1 + s * L::T_BYTES + c * 8192, &tmT1, &t_full[s], col0, c, h, row, p.pad3d);
+                    tma_load_head(sT2 + s * L::T_BYTES + c * 8192, &tmT2, &t_full[s], DKV ? col0_do : col0, c, h, row, p.pad3d);
                 }
             }
         }
@@ -630,7 +641,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                         o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * mul, __uint_as_float(v[g * 8 + 3]) * mul);
                         o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * mul, __uint_as_float(v[g * 8 + 5]) * mul);
                         o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * mul, __uint_as_float(v[g * 8 + 7]) * mul);
-                        st_v4(orow + c * 32 + g * 8, o);
+                        if (half * DH + c * 32 + g * 8 < p.d_real) st_v4(orow + c * 32 + g * 8, o);
                     }
                 }
             }
@@ -1004,7 +1015,7 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
 // ---------------------------------------------------------------------------------------------------------------
 static int check_common(const b200_attn_args* a, const char* who) {
     B200_REQUIRE(a != nullptr, "%s: null args", who);
-    B200_REQUIRE(a->D == 64 || a->D == 128 || a->D == 256, "%s: head_dim %d unsupported (64, 128, 256)", who, a->D);
+    B200_REQUIRE(a->D == 64 || a->D == 80 || a->D == 128 || a->D == 256, "%s: head_dim %d unsupported (64, 80, 128, 256)", who, a->D);
     B200_REQUIRE(a->B > 0 && a->S > 0 && a->H > 0, "%s: bad B/S/H", who);
     B200_REQUIRE(a->qkv_row_stride % 8 == 0 && a->qkv_head_stride % 8 == 0, "%s: q/k/v strides must be multiples of 8 elements", who);
     B200_REQUIRE(a->o_row_stride % 8 == 0 && a->o_head_stride % 8 == 0 && aligned16(a->o), "%s: o must be 16B aligned with strides %% 8 == 0", who);
@@ -1012,7 +1023,11 @@ static int check_common(const b200_attn_args* a, const char* who) {
     return 0;
 }
 
+static inline bool padded_head(const b200_attn_args* a) { return a->D % 64 != 0; }
+
 static int qkv_tmap(CUtensorMap* m, const void* ptr, const b200_attn_args* a, int64_t row_stride, int64_t head_stride, uint32_t box_rows) {
+    if (padded_head(a))
+        return make_tmap_bf16_3d(m, ptr, a->D, a->H, static_cast<uint64_t>(a->B) * a->S, head_stride, row_stride, 64, box_rows);
     const uint64_t inner = static_cast<uint64_t>(a->H - 1) * head_stride + a->D;
     return make_tmap_bf16_2d(m, ptr, inner, static_cast<uint64_t>(a->B) * a->S, row_stride, 64, box_rows);
 }
@@ -1032,6 +1047,8 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.dv = static_cast<__nv_bfloat16*>(a->dv);
     p.dqkv_row_stride = a->dqkv_row_stride, p.dqkv_head_stride = a->dqkv_head_stride;
     p.p_out = nullptr, p.ds_out = nullptr;
+    p.d_real = a->D;
+    p.pad3d = padded_head(a) ? 1 : 0;
     static const int tr = getenv("B200_ATTN_TRACE") ? 1 : 0;
     p.trace = tr;
     return p;
@@ -1158,6 +1175,7 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
     cudaStream_t st = as_stream(stream);
     switch (a->D) {
         case 64: return launch_fwd<64, 128, 2>(a, st);
+        case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: return launch_fwd<256, 64, 2>(a, st);
     }
@@ -1183,6 +1201,7 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
         case 64:
             if ((rc = launch_bwd<64, 64, 2, false>(a, st))) return rc;
             return launch_bwd<64, 64, 2, true>(a, st);
+        case 80:
         case 128:
             if ((rc = launch_bwd<128, 128, 2, false>(a, st))) return rc;
             return launch_bwd<128, 128, 2, true>(a, st);

@@ -524,6 +524,30 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
 
 
 // deepest ring <= STAGES that still fits next to the GELU variant's second output slab
+// 3-D bf16 map {d, head, token} with 128B swizzle: a head whose width is not a multiple of 64 (head_dim 80) is read as
+// zero-padded 64-wide boxes, because the box is clipped at the extent of dimension 0 (attention.cu).
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_elems,
+                      uint64_t pitch2_elems, uint32_t box0, uint32_t box2) {
+    int rc = resolve_driver();
+    if (rc) return rc;
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(0);
+        ctx_bound = true;
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (pitch1_elems * 2) % 16 != 0 || (pitch2_elems * 2) % 16 != 0)
+        return fail(-1, "tensor map 3d: base must be 16B aligned and pitches multiples of 8 elements");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
+    cuuint32_t box[3] = {box0, 1, box2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+    return 0;
+}
+
 template <int BN, int STAGES, int CG>
 constexpr int gelu_stages() {
     int st = STAGES;

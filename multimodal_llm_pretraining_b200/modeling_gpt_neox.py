@@ -135,8 +135,8 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         self.L = cfg.num_hidden_layers
         self.V = cfg.vocab_size
         self.inter = cfg.intermediate_size
-        if self.hd not in (64, 128, 256):
-            raise NotImplementedError(f"head_dim {self.hd} has no tcgen05 attention kernel yet (built: 64, 128, 256)")
+        if self.hd not in (64, 80, 128, 256):
+            raise NotImplementedError(f"head_dim {self.hd} has no tcgen05 attention kernel yet (built: 64, 80, 128, 256)")
 
         self.flat = FlatParams(neox_param_shapes(cfg))
         f = self.flat

@@ -44,6 +44,9 @@ CASES = [
     (1, 2048, 2, 64, True, True),
     (2, 512, 2, 256, False, True),   # head_dim 256, bidirectional, score-scratch path
     (2, 768, 3, 256, True, True),    # three 256-key tiles per head
+    (2, 256, 4, 80, True, True),     # Pythia-2.8b head_dim 80: zero-padded to 128 by 3-D tensor maps
+    (1, 200, 2, 80, True, True),
+    (1, 384, 2, 80, False, False),
 ]
 
 

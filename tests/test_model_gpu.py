@@ -94,7 +94,7 @@ def test_three_adam_steps_vs_hf_golden(gold, dev):
         assert rel(upd_got, upd_ref) <= 0.15, (k, rel(upd_got, upd_ref))
 
 
-@pytest.mark.parametrize("nh,h", [(2, 256), (1, 256)])  # head_dim 128 and 256 (Pythia-1.4b / Pythia-1b head shapes)
+@pytest.mark.parametrize("nh,h", [(2, 256), (1, 256), (4, 320)])  # head_dim 128, 256, 80 (Pythia-1.4b / 1b / 2.8b head shapes)
 def test_loss_and_grads_vs_oracle_other_head_dims(dev, nh, h):
     cfg = dict(vocab_size=512, hidden_size=h, num_hidden_layers=2, num_attention_heads=nh, intermediate_size=4 * h,
                rotary_pct=0.25, rotary_emb_base=10000, layer_norm_eps=1e-5)
