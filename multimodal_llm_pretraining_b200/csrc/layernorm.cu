@@ -113,6 +113,111 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1,
     }
 }
 
+
+// Persistent forward: a row is owned by G consecutive warps, a block holds 8 / G row groups and walks rows
+// (row = (it * grid + block) * groups + group). Each lane owns the same NV 16-byte column vectors for every row it visits, so the
+// affine parameters of those columns are loaded ONCE into registers; re-reading 4 fp32 parameter vectors per 8 activations
+// through L1 for every row cost more LSU cycles than the activation traffic itself.
+__device__ __forceinline__ float group_sum_bar(float v, int G, float* red, int grp) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 0) red[warp] = v;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(G * 32) : "memory");
+    float t = 0.f;
+    for (int j = 0; j < G; ++j) t += red[grp * G + j];
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(G * 32) : "memory");
+    return t;
+}
+
+template <int NV, int NA>
+__global__ void __launch_bounds__(256)
+ln_fwd_persist_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
+                      __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
+                      __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                      int cols, float eps, int G) {
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = 8 / G;
+    const int grp = warp / G, sub = warp % G;
+    const float inv_cols = 1.0f / cols;
+
+    float ga[NA][NV * 8], be[NA][NV * 8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = ((i * G + sub) * 32 + lane) * 8;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            const float* gp = a == 0 ? g1 : g2;
+            const float* bp = a == 0 ? b1 : b2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                ga[a][i * 8 + j] = col < cols ? __ldg(gp + col + j) : 0.f;
+                be[a][i * 8 + j] = col < cols ? __ldg(bp + col + j) : 0.f;
+            }
+        }
+    }
+    const int n_iter = (rows + groups * gridDim.x - 1) / (groups * gridDim.x);
+    uint4 raw[NV];  // next row's vectors: issued one iteration ahead so that their latency overlaps the reductions / stores
+    auto load_row = [&](int it) {
+        const int row = (it * gridDim.x + blockIdx.x) * groups + grp;
+        const size_t roff = static_cast<size_t>(row) * cols;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = ((i * G + sub) * 32 + lane) * 8;
+            raw[i] = (row < rows && col < cols) ? ld_nc_v4(x + roff + col) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    if (n_iter > 0) load_row(0);
+    for (int it = 0; it < n_iter; ++it) {
+        const int row = (it * gridDim.x + blockIdx.x) * groups + grp;
+        const bool row_ok = row < rows;
+        const size_t roff = static_cast<size_t>(row) * cols;
+        float xf[NV * 8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = bf2_to_f2(w[j]);
+                xf[i * 8 + 2 * j] = f.x, xf[i * 8 + 2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+        if (it + 1 < n_iter) load_row(it + 1);
+        const float mean = group_sum_bar(sum, G, red, grp) * inv_cols;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = ((i * G + sub) * 32 + lane) * 8;
+            if (col < cols) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sq += (xf[i * 8 + j] - mean) * (xf[i * 8 + j] - mean);
+            }
+        }
+        const float rstd = rsqrtf(group_sum_bar(sq, G, red, grp) * inv_cols + eps);
+        if (row_ok && sub == 0 && lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int col = ((i * G + sub) * 32 + lane) * 8;
+                if (col < cols) {
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = fmaf((xf[i * 8 + j] - mean) * rstd, ga[a][i * 8 + j], be[a][i * 8 + j]);
+                        st_v4((a == 0 ? y1 : y2) + roff + col, make_uint4(f2_to_bf2(o[0], o[1]), f2_to_bf2(o[2], o[3]), f2_to_bf2(o[4], o[5]), f2_to_bf2(o[6], o[7])));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Backward.  Persistent: one 256-thread block per SM loops over rows; each lane accumulates dgamma/dbeta for the
 // columns it owns in registers, block partials go to the workspace, ln_bwd_finalize sums them deterministically and
@@ -137,7 +242,38 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
 #pragma unroll
         for (int i = 0; i < NV * 8; ++i) acc_g[a][i] = 0.f, acc_b[a][i] = 0.f;
 
+    // affine weights of this lane's columns: loaded once (they were re-read through L1 for every row)
+    float gam[NA][NV * 8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int col = ((i * G + sub) * 32 + lane) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            gam[0][i * 8 + j] = col < cols ? __ldg(g1 + col + j) : 0.f;
+            if (NA == 2) gam[NA - 1][i * 8 + j] = col < cols ? __ldg(g2 + col + j) : 0.f;
+        }
+    }
     const int n_iter = (rows + rows_per_block * gridDim.x - 1) / (rows_per_block * gridDim.x);
+    // software pipeline: the loads of row it+1 are issued before the reductions / stores of row it, which doubles the bytes
+    // in flight per SM (one block per SM, and each row is only a few KB per operand)
+    uint4 rx[NV], r1[NV], r2[NV], rr[NV];
+    auto load_row = [&](int it) {
+        const int row = (it * gridDim.x + blockIdx.x) * rows_per_block + slot;
+        const size_t roff = static_cast<size_t>(row) * cols;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int col = ((i * G + sub) * 32 + lane) * 8;
+            const bool ok = row < rows && col < cols;
+            rx[i] = r1[i] = r2[i] = rr[i] = make_uint4(0, 0, 0, 0);
+            if (ok) {
+                rx[i] = ld_nc_v4(x + roff + col);
+                r1[i] = ld_nc_v4(dy1 + roff + col);
+                if (NA == 2) r2[i] = ld_nc_v4(dy2 + roff + col);
+                if (dres != nullptr) rr[i] = ld_nc_v4(dres + roff + col);
+            }
+        }
+    };
+    if (n_iter > 0) load_row(0);
     for (int it = 0; it < n_iter; ++it) {
         const int row = (it * gridDim.x + blockIdx.x) * rows_per_block + slot;
         const bool row_ok = row < rows;
@@ -145,48 +281,32 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
         const float mean = row_ok ? mean_in[row] : 0.f;
         const float rstd = row_ok ? rstd_in[row] : 0.f;
 
-        float xh[NV * 8], dxh[NV * 8];
+        float xh[NV * 8], dxh[NV * 8], res[NV * 8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int col = ((i * G + sub) * 32 + lane) * 8;
             const bool ok = row_ok && col < cols;
-            uint4 xv = make_uint4(0, 0, 0, 0), d1 = xv, d2 = xv;
-            if (ok) {
-                xv = ld_nc_v4(x + roff + col);
-                d1 = ld_nc_v4(dy1 + roff + col);
-                if (NA == 2) d2 = ld_nc_v4(dy2 + roff + col);
-            }
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-            const uint32_t w1[4] = {d1.x, d1.y, d1.z, d1.w};
-            const uint32_t w2[4] = {d2.x, d2.y, d2.z, d2.w};
-            float ga[8], gb[8];
-            if (ok) {
-                *reinterpret_cast<float4*>(&ga[0]) = __ldg(reinterpret_cast<const float4*>(g1 + col));
-                *reinterpret_cast<float4*>(&ga[4]) = __ldg(reinterpret_cast<const float4*>(g1 + col + 4));
-                if (NA == 2) {
-                    *reinterpret_cast<float4*>(&gb[0]) = __ldg(reinterpret_cast<const float4*>(g2 + col));
-                    *reinterpret_cast<float4*>(&gb[4]) = __ldg(reinterpret_cast<const float4*>(g2 + col + 4));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) ga[j] = 0.f, gb[j] = 0.f;
-            }
+            const uint32_t xw[4] = {rx[i].x, rx[i].y, rx[i].z, rx[i].w};
+            const uint32_t w1[4] = {r1[i].x, r1[i].y, r1[i].z, r1[i].w};
+            const uint32_t w2[4] = {r2[i].x, r2[i].y, r2[i].z, r2[i].w};
+            const uint32_t wr[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 xf = bf2_to_f2(xw[j]);
                 const float2 a = bf2_to_f2(w1[j]);
+                const float2 rf = bf2_to_f2(wr[j]);
                 const float h0 = ok ? (xf.x - mean) * rstd : 0.f;
                 const float h1 = ok ? (xf.y - mean) * rstd : 0.f;
-                float t0 = a.x * ga[2 * j], t1 = a.y * ga[2 * j + 1];
+                float t0 = a.x * gam[0][i * 8 + 2 * j], t1 = a.y * gam[0][i * 8 + 2 * j + 1];
                 acc_g[0][i * 8 + 2 * j] += a.x * h0;
                 acc_g[0][i * 8 + 2 * j + 1] += a.y * h1;
                 acc_b[0][i * 8 + 2 * j] += a.x;
                 acc_b[0][i * 8 + 2 * j + 1] += a.y;
                 if (NA == 2) {
                     const float2 b = bf2_to_f2(w2[j]);
-                    t0 += b.x * gb[2 * j];
-                    t1 += b.y * gb[2 * j + 1];
+                    t0 += b.x * gam[NA - 1][i * 8 + 2 * j];
+                    t1 += b.y * gam[NA - 1][i * 8 + 2 * j + 1];
                     acc_g[NA - 1][i * 8 + 2 * j] += b.x * h0;
                     acc_g[NA - 1][i * 8 + 2 * j + 1] += b.y * h1;
                     acc_b[NA - 1][i * 8 + 2 * j] += b.x;
@@ -196,10 +316,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
                 xh[i * 8 + 2 * j + 1] = h1;
                 dxh[i * 8 + 2 * j] = t0;
                 dxh[i * 8 + 2 * j + 1] = t1;
+                res[i * 8 + 2 * j] = rf.x;
+                res[i * 8 + 2 * j + 1] = rf.y;
                 s1 += t0 + t1;
                 s2 += t0 * h0 + t1 * h1;
             }
         }
+        if (it + 1 < n_iter) load_row(it + 1);
         s1 = group_sum(s1, G, red) * inv_cols;
         s2 = group_sum(s2, G, red) * inv_cols;
         if (row_ok) {
@@ -209,17 +332,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
                 if (col < cols) {
                     float r[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = rstd * (dxh[i * 8 + j] - s1 - xh[i * 8 + j] * s2);
-                    if (dres != nullptr) {
-                        const uint4 dv = ld_nc_v4(dres + roff + col);
-                        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 f = bf2_to_f2(dw[j]);
-                            r[2 * j] += f.x;
-                            r[2 * j + 1] += f.y;
-                        }
-                    }
+                    for (int j = 0; j < 8; ++j) r[j] = fmaf(rstd, dxh[i * 8 + j] - s1 - xh[i * 8 + j] * s2, res[i * 8 + j]);
                     uint4 o;
                     o.x = f2_to_bf2(r[0], r[1]);
                     o.y = f2_to_bf2(r[2], r[3]);
@@ -291,23 +404,27 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
     B200_REQUIRE(cols <= 8192, "layernorm_fwd: cols %d > 8192 unsupported", cols);
     B200_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm_fwd: pointers must be 16-byte aligned");
     B200_REQUIRE((gamma2 == nullptr) == (y2 == nullptr) && (gamma2 == nullptr) == (beta2 == nullptr), "layernorm_fwd: gamma2/beta2/y2 must be all set or all NULL");
-    const int G = pick_group(cols, 2048, 4);
-    const int nv = (cols + 256 * G - 1) / (256 * G);
-    const int rows_per_block = 4 / G;
-    dim3 grid((rows + rows_per_block - 1) / rows_per_block);
     auto xs = static_cast<const __nv_bfloat16*>(x);
     auto y1s = static_cast<__nv_bfloat16*>(y);
     auto y2s = static_cast<__nv_bfloat16*>(y2);
     cudaStream_t st = as_stream(stream);
-#define LAUNCH(NVV) ln_fwd_kernel<NVV><<<grid, 128, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G)
+    // G warps per row: 4 up to 3072 columns (<= 3 vectors per lane keeps the register-resident parameters small), else 8
+    const int G = cols <= 3072 ? 4 : 8;
+    const int nv = (cols + 256 * G - 1) / (256 * G);
+    const int groups = 8 / G;
+    int grid = num_sms() * 2;  // two 256-thread blocks per SM are resident (<= 128 registers per thread)
+    const int max_blocks = (rows + groups - 1) / groups;
+    if (grid > max_blocks) grid = max_blocks;
+#define LAUNCH(NVV)                                                                                                                   \
+    do {                                                                                                                              \
+        if (gamma2) ln_fwd_persist_kernel<NVV, 2><<<grid, 256, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G); \
+        else ln_fwd_persist_kernel<NVV, 1><<<grid, 256, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G);        \
+    } while (0)
     switch (nv) {
         case 1: LAUNCH(1); break;
         case 2: LAUNCH(2); break;
         case 3: LAUNCH(3); break;
         case 4: LAUNCH(4); break;
-        case 5: LAUNCH(5); break;
-        case 6: LAUNCH(6); break;
-        case 7: case 8: LAUNCH(8); break;
         default: return fail(-1, "layernorm_fwd: unsupported cols %d", cols);
     }
 #undef LAUNCH
