@@ -61,6 +61,7 @@ struct AttnParams {
     int64_t dqkv_row_stride, dqkv_head_stride;
     __nv_bfloat16* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
     int trace;
+    const __nv_bfloat16* d_o;  // score pass: delta = rowsum(dO * O) is computed in its prologue (no separate pre-pass)
     int d_real;  // head_dim as stored (80 for Pythia-2.8b); the kernels run on D = d_real rounded up to 64/128/256 with the
     int pad3d;   // tail columns zero-filled by 3-D TMA maps {d, head, token} (pad3d = 1) and clipped again on store
     __nv_bfloat16* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
@@ -321,6 +322,294 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // =================================================================================================================
+// forward, head_dim 256
+// =================================================================================================================
+// Same algorithm as attn_fwd_kernel, re-laid-out for the one head size where shared memory is the constraint:
+//   * Q (128 x 256 bf16) lives in TMEM (128 columns) and feeds S = Q K^T as the A operand of a TS-mode MMA: it costs no shared
+//     memory and the S MMAs read only the 2 KB K slice per step instead of 6 KB (they were shared-memory-bandwidth bound);
+//   * the 64 KB that frees up hold 3 K stages + 3 V stages (32 KB each) instead of 2 shared K/V stages, and a K stage is
+//     released as soon as S_j retires (V only after P V_j): with ~2000-clock TMA latency the old ring stalled every tile;
+//   * producer and MMA issuer poll their inputs and serve whichever is ready.
+// TMEM: O [0,256) | S double buffer [256,384) | Q bf16 [384,512).   smem: P 16 KB | K x3 | V x3 = 208 KB.
+struct Fwd256Smem {
+    static constexpr uint32_t OFF_P = 0;  // two P tiles: softmax of block j+1 writes one while P V_j reads the other
+    static constexpr uint32_t OFF_K = 32768;
+    static constexpr uint32_t OFF_V = OFF_K + 3 * 32768;
+    static constexpr uint32_t OFF_BAR = OFF_V + 3 * 32768;
+    static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __nv_bfloat16* __restrict__ qptr, int64_t q_row_stride, const AttnParams p) {
+    using L = Fwd256Smem;
+    constexpr int D = 256, BN = 64, NSUB = 4, NST = 3;
+    constexpr uint32_t TM_O = 0, TM_S = 256, TM_Q = 384;
+    constexpr uint32_t KV_BYTES = 32768;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sP = smem + L::OFF_P;
+    uint8_t* sK = smem + L::OFF_K;
+    uint8_t* sV = smem + L::OFF_V;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* q_ready = bars;          // 1 (4 warp arrivals)
+    uint64_t* k_full = bars + 1;       // 3
+    uint64_t* k_empty = bars + 4;      // 3
+    uint64_t* v_full = bars + 7;       // 3
+    uint64_t* v_empty = bars + 10;     // 3
+    uint64_t* s_full = bars + 13;      // 2
+    uint64_t* s_free = bars + 15;      // 2 (4 warp arrivals)
+    uint64_t* p_ready = bars + 17;     // 1 (4 warp arrivals)
+    uint64_t* o_done = bars + 18;      // 2: o_done[b] = the P V that read P buffer b has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * 128;
+    const int kv_end = p.causal ? min(p.S, q0 + 128) : p.S;
+    const int n_blocks = (kv_end + BN - 1) / BN;
+    const int col0 = h * static_cast<int>(p.qkv_head_stride);
+    const int row_base = b * p.S;
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(q_ready, 4);
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_free[s], 4);
+        }
+        mbar_init(p_ready, 4);
+        mbar_init(&o_done[0], 1);
+        mbar_init(&o_done[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ---------------------------------------------------------------- TMA producer: two in-order rings, served as they free up
+        if (elect_one()) {
+            int next_k = 0, next_v = 0;
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_k < n_blocks || next_v < n_blocks) {
+                bool progressed = false;
+                if (next_k < n_blocks && mbar_try_wait(&k_empty[next_k % NST], ((next_k / NST) & 1) ^ 1)) {
+                    const int s = next_k % NST;
+                    mbar_expect_tx(&k_full[s], KV_BYTES);
+                    for (int c = 0; c < NSUB; ++c) tma_load_2d(sK + s * KV_BYTES + c * 8192, &tmK, &k_full[s], col0 + c * 64, row_base + next_k * BN);
+                    ++next_k, progressed = true;
+                }
+                if (next_v < n_blocks && mbar_try_wait(&v_empty[next_v % NST], ((next_v / NST) & 1) ^ 1)) {
+                    const int s = next_v % NST;
+                    mbar_expect_tx(&v_full[s], KV_BYTES);
+                    for (int c = 0; c < NSUB; ++c) tma_load_2d(sV + s * KV_BYTES + c * 8192, &tmV, &v_full[s], col0 + c * 64, row_base + next_v * BN);
+                    ++next_v, progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention fwd256 producer stalled (block %d,%d,%d k %d v %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, next_k, next_v);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, false, false);  // S = Q K^T (A = Q from TMEM)
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);    // O += P V (V MN-major)
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 8192, 1024);
+            const uint64_t p_desc = umma_desc_sw128(smem_u32(sP), 16, 1024);
+            auto issue_s = [&](int j) {
+                const int s = j % NST;
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((s * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ts(tmem + TM_S + (j & 1) * BN, tmem + TM_Q + kk * 8, kd + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
+                tc_commit(&k_empty[s]);  // K_j is dead as soon as S_j retires
+                tc_commit(&s_full[j & 1]);
+            };
+            auto issue_pv = [&](int j) {
+                const int s = j % NST;
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk)
+                    umma_ss(tmem + TM_O, p_desc + static_cast<uint64_t>(((j & 1) * 16384 + kk * 32) >> 4), vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_o,
+                            (j | kk) != 0);
+                tc_commit(&v_empty[s]);
+                tc_commit(&o_done[j & 1]);
+            };
+            mbar_wait(q_ready, 0);
+            tc_fence_after();
+            int next_s = 0, next_pv = 0;  // S_j needs K_j and a free S buffer; P V_j needs P_j and V_j
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_pv < n_blocks) {
+                bool progressed = false;
+                if (next_s < n_blocks && next_s <= next_pv + 1 && mbar_try_wait(&k_full[next_s % NST], (next_s / NST) & 1) &&
+                    (next_s < 2 || mbar_try_wait(&s_free[next_s & 1], ((next_s >> 1) - 1) & 1))) {
+                    tc_fence_after();
+                    trace_evt(tr, 4096 + 16 * next_s + 0);
+                    issue_s(next_s);
+                    ++next_s, progressed = true;
+                }
+                if (next_pv < next_s && mbar_try_wait(p_ready, next_pv & 1) && mbar_try_wait(&v_full[next_pv % NST], (next_pv / NST) & 1)) {
+                    tc_fence_after();
+                    trace_evt(tr, 4096 + 16 * next_pv + 1);
+                    issue_pv(next_pv);
+                    ++next_pv, progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention fwd256 issuer stalled (block %d,%d,%d s %d pv %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, next_s, next_pv);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane
+        const int r = warp * 32 + lane;
+        const int q_idx = q0 + r;
+        const bool row_ok = q_idx < p.S;
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const float sl2 = p.scale * LOG2E_F;
+        {
+            const __nv_bfloat16* qrow = qptr + static_cast<size_t>(row_base + (row_ok ? q_idx : q0)) * q_row_stride + col0;
+            uint4 u[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = row_ok ? ld_nc_v4(qrow + i * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i * 4 + 0] = u[c * 8 + i].x, v[i * 4 + 1] = u[c * 8 + i].y, v[i * 4 + 2] = u[c * 8 + i].z, v[i * 4 + 3] = u[c * 8 + i].w;
+                tmem_st_32x32(lane_addr + TM_Q + c * 32, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+        }
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < n_blocks; ++j) {
+            const bool tr0 = tr && threadIdx.x == 0;
+            trace_evt(tr0, 4096 + 16 * j + 8);
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            trace_evt(tr0, 4096 + 16 * j + 9);
+            uint32_t sv[64];
+            tmem_ld_32x32(lane_addr + TM_S + (j & 1) * BN, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32(lane_addr + TM_S + (j & 1) * BN + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[j & 1]);
+            const int kv0 = j * BN;
+            if ((kv0 + BN > p.S) || (p.causal && kv0 + BN - 1 > q0)) {
+                const int lim = p.causal ? min(p.S - 1, q_idx) : p.S - 1;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) sv[i] = (kv0 + i > lim) ? 0xff800000u : sv[i];
+            }
+            float mx = __uint_as_float(sv[0]);
+#pragma unroll
+            for (int i = 1; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            mx *= sl2;
+            const float m_new = fmaxf(m_used, mx);
+            const bool need = m_new > m_used + 8.0f;  // lazy rescale: only when the running max grew by > 2^8
+            // P buffer j & 1 was last read by P V_{j-2}
+            trace_evt(tr0, 4096 + 16 * j + 10);
+            if (j >= 2) mbar_wait(&o_done[j & 1], ((j >> 1) - 1) & 1);
+            trace_evt(tr0, 4096 + 16 * j + 11);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                // rescaling O races with an in-flight P V: wait for the latest one (rare: the max must grow by > 2^8)
+                mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                {
+                    const float alpha = need ? ex2(m_used - m_new) : 1.0f;
+                    l *= alpha;
+#pragma unroll 1
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(lane_addr + TM_O + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32(lane_addr + TM_O + c * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            if (need) m_used = m_new;
+            const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < BN / 8; ++cc) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = ex2(fmaf(__uint_as_float(sv[cc * 8 + i]), sl2, neg_m));
+                    sum += e[i];
+                }
+                st_shared_v4(sP + (j & 1) * 16384 + sw128_offset(r, cc), make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
+            }
+            l += sum;
+            trace_evt(tr0, 4096 + 16 * j + 12);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+            trace_evt(tr0, 4096 + 16 * j + 13);
+        }
+        // ---- epilogue: O / l -> bf16, LSE
+        mbar_wait(&o_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1);
+        tc_fence_after();
+        const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+        __nv_bfloat16* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + TM_O + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    o.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+                    o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+                    o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+                    o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+                    st_v4(orow + c * 32 + g * 8, o);
+                }
+            }
+        }
+        if (row_ok) p.lse[(static_cast<size_t>(b) * p.H + h) * p.S + q_idx] = (m_used + log2f(l)) * LN2_F;
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// =================================================================================================================
 // backward
 // =================================================================================================================
 // delta[b,h,s] = sum_d dO * O ; one warp per (token, head)
@@ -365,7 +654,7 @@ struct BwdSmem {
     static constexpr uint32_t OFF_A2 = OFF_A1 + 16384;
     static constexpr uint32_t OFF_STAT = OFF_A2 + (DKV ? 16384 : 0);
     static constexpr uint32_t OFF_BAR = OFF_STAT + (DKV ? 512 : 0);
-    static constexpr uint32_t TOTAL = OFF_BAR + 128 + 1024;
+    static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
 // DKV=false: resident R1=Q_i, R2=dO_i ; streamed T1=K_j, T2=V_j ; out dQ (all D columns).
@@ -875,6 +1164,8 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
         const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.S;
         // rows beyond S: lse = +inf makes every P (and dS) of the row exactly 0
         const float neg_lse2 = row_ok ? -p.lse[stat_base + r_idx] * LOG2E_F : -INFINITY;
+        // (computing delta = rowsum(dO * O) here instead of in the pre-pass was tried: the extra 64 loads per thread sit on the
+        // CTA's un-overlapped prologue and cost 0.2 ms per layer against the 0.06 ms of the separate kernel)
         const float my_delta = row_ok ? p.delta[stat_base + r_idx] : 0.f;
         const int S_ = p.S;
         const bool causal_ = p.causal != 0;
@@ -1047,6 +1338,7 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.dv = static_cast<__nv_bfloat16*>(a->dv);
     p.dqkv_row_stride = a->dqkv_row_stride, p.dqkv_head_stride = a->dqkv_head_stride;
     p.p_out = nullptr, p.ds_out = nullptr;
+    p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
     p.d_real = a->D;
     p.pad3d = padded_head(a) ? 1 : 0;
     static const int tr = getenv("B200_ATTN_TRACE") ? 1 : 0;
@@ -1075,6 +1367,20 @@ static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
     dim3 grid((a->S + 127) / 128, a->H, a->B);
     kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, make_params(a));
     return check_launch("attention_fwd");
+}
+
+static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
+    using L = Fwd256Smem;
+    static_assert(L::TOTAL <= 232448, "fwd256 smem budget");
+    CUtensorMap tk, tv;
+    int rc;
+    if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    auto kern = attn_fwd256_kernel;
+    if ((rc = set_smem(kern, L::TOTAL, "attention_fwd256"))) return rc;
+    dim3 grid((a->S + 127) / 128, a->H, a->B);
+    kern<<<grid, 192, L::TOTAL, st>>>(tk, tv, static_cast<const __nv_bfloat16*>(a->q), a->qkv_row_stride, make_params(a));
+    return check_launch("attention_fwd256");
 }
 
 template <int D, int DH, int STAGES, bool DKV>
@@ -1174,10 +1480,14 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
     B200_REQUIRE(a->lse != nullptr, "attention_fwd: lse is required");
     cudaStream_t st = as_stream(stream);
     switch (a->D) {
-        case 64: return launch_fwd<64, 128, 2>(a, st);
+        // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
+        case 64: return launch_fwd<64, 128, 5>(a, st);
         case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
-        default: return launch_fwd<256, 64, 2>(a, st);
+        default: {
+            static const bool old_fwd = getenv("B200_ATTN_OLD_FWD") != nullptr;  // perf triage only
+            return old_fwd ? launch_fwd<256, 64, 2>(a, st) : launch_fwd256(a, st);
+        }
     }
 }
 
@@ -1188,6 +1498,8 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
     B200_REQUIRE(a->dqkv_row_stride % 8 == 0 && a->dqkv_head_stride % 8 == 0 && aligned16(a->dq) && aligned16(a->dk) && aligned16(a->dv) && aligned16(a->d_o),
                  "attention_bwd: gradient buffers must be 16B aligned with strides %% 8 == 0");
     cudaStream_t st = as_stream(stream);
+    static const bool old_dq = getenv("B200_ATTN_OLD_DQ") != nullptr;  // perf triage only
+    const bool score_path = a->D == 256 && a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0;
     {
         const int64_t total_warps = static_cast<int64_t>(a->B) * a->S * a->H;
         int64_t blocks = (total_warps + 7) / 8;
@@ -1199,19 +1511,18 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
     }
     switch (a->D) {
         case 64:
-            if ((rc = launch_bwd<64, 64, 2, false>(a, st))) return rc;
-            return launch_bwd<64, 64, 2, true>(a, st);
+            if ((rc = launch_bwd<64, 64, 8, false>(a, st))) return rc;
+            return launch_bwd<64, 64, 8, true>(a, st);
         case 80:
         case 128:
-            if ((rc = launch_bwd<128, 128, 2, false>(a, st))) return rc;
-            return launch_bwd<128, 128, 2, true>(a, st);
+            if ((rc = launch_bwd<128, 128, 4, false>(a, st))) return rc;
+            return launch_bwd<128, 128, 4, true>(a, st);
         default:
-            if (a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0) {
+            if (score_path) {
                 // head_dim 256: the dQ pass also writes its P / dS tiles; dK and dV become batched causal GEMMs (5 matmul
                 // units instead of the 9 a TMEM-limited fused dK/dV pass needs at this head size)
                 B200_REQUIRE(aligned16(a->p_scratch) && aligned16(a->ds_scratch), "attention_bwd: score scratch must be 16B aligned");
                 B200_REQUIRE(static_cast<int64_t>(a->B) * a->H * a->S < (1ll << 31), "attention_bwd: B*H*S too large for the score scratch path");
-                static const bool old_dq = getenv("B200_ATTN_OLD_DQ") != nullptr;  // perf triage only
                 if ((rc = old_dq ? launch_bwd<256, 256, 1, false>(a, st, true) : launch_bwd_dq256(a, st))) return rc;
                 return dkv_from_scores(a, st);
             }
