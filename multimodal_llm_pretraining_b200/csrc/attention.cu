@@ -340,8 +340,8 @@ struct Fwd256Smem {
 };
 
 __global__ void __launch_bounds__(192, 1)
-attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __nv_bfloat16* __restrict__ qptr, int64_t q_row_stride, const AttnParams p) {
+attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
     using L = Fwd256Smem;
     constexpr int D = 256, BN = 64, NSUB = 4, NST = 3;
     constexpr uint32_t TM_O = 0, TM_S = 256, TM_Q = 384;
@@ -362,7 +362,9 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     uint64_t* s_free = bars + 15;      // 2 (4 warp arrivals)
     uint64_t* p_ready = bars + 17;     // 1 (4 warp arrivals)
     uint64_t* o_done = bars + 18;      // 2: o_done[b] = the P V that read P buffer b has retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* q_full = bars + 20;      // 1: the Q tile has landed in its staging area (V stages 1 and 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint8_t* sQst = sV + KV_BYTES;     // 64 KB staging of the Q tile on its way to TMEM
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
@@ -372,7 +374,9 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     const int n_blocks = (kv_end + BN - 1) / BN;
     const int col0 = h * static_cast<int>(p.qkv_head_stride);
     const int row_base = b * p.S;
-    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const bool tr = (p.trace == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ||
+                    (p.trace == 2 && blockIdx.x == 0 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1);
+    if (tr && threadIdx.x == 0) g_attn_trace[8000] = clock64(), g_attn_trace[8006] = globaltimer_ns();
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmK);
@@ -391,6 +395,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         mbar_init(p_ready, 4);
         mbar_init(&o_done[0], 1);
         mbar_init(&o_done[1], 1);
+        mbar_init(q_full, 1);
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -401,22 +406,28 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (tr && threadIdx.x == 0) g_attn_trace[8001] = clock64();
 
     if (warp == 4) {
         // ---------------------------------------------------------------- TMA producer: two in-order rings, served as they free up
         if (elect_one()) {
+            // Q tile -> staging (full 128-byte lines through TMA; per-thread row loads of a [rows x 512 B] tile took 20k clocks)
+            mbar_expect_tx(q_full, 65536);
+            for (int c = 0; c < NSUB; ++c) tma_load_2d(sQst + c * 16384, &tmQ, q_full, col0 + c * 64, row_base + q0);
+            bool q_moved = false;  // V stages 1 and 2 are free once the softmax warps have copied Q into TMEM
             int next_k = 0, next_v = 0;
             const uint64_t t_start = globaltimer_ns();
             uint32_t spins = 0;
             while (next_k < n_blocks || next_v < n_blocks) {
                 bool progressed = false;
+                if (!q_moved) q_moved = mbar_try_wait(q_ready, 0);
                 if (next_k < n_blocks && mbar_try_wait(&k_empty[next_k % NST], ((next_k / NST) & 1) ^ 1)) {
                     const int s = next_k % NST;
                     mbar_expect_tx(&k_full[s], KV_BYTES);
                     for (int c = 0; c < NSUB; ++c) tma_load_2d(sK + s * KV_BYTES + c * 8192, &tmK, &k_full[s], col0 + c * 64, row_base + next_k * BN);
                     ++next_k, progressed = true;
                 }
-                if (next_v < n_blocks && mbar_try_wait(&v_empty[next_v % NST], ((next_v / NST) & 1) ^ 1)) {
+                if (next_v < n_blocks && (q_moved || next_v % NST == 0) && mbar_try_wait(&v_empty[next_v % NST], ((next_v / NST) & 1) ^ 1)) {
                     const int s = next_v % NST;
                     mbar_expect_tx(&v_full[s], KV_BYTES);
                     for (int c = 0; c < NSUB; ++c) tma_load_2d(sV + s * KV_BYTES + c * 8192, &tmV, &v_full[s], col0 + c * 64, row_base + next_v * BN);
@@ -491,21 +502,23 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         const float sl2 = p.scale * LOG2E_F;
         {
-            const __nv_bfloat16* qrow = qptr + static_cast<size_t>(row_base + (row_ok ? q_idx : q0)) * q_row_stride + col0;
-            uint4 u[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] = row_ok ? ld_nc_v4(qrow + i * 8) : make_uint4(0, 0, 0, 0);
+            // Q row: staging tile (SWIZZLE_128B, 4 sub-tiles of 64 columns) -> registers -> TMEM (bf16 pairs, 128 columns)
+            mbar_wait(q_full, 0);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i * 4 + 0] = u[c * 8 + i].x, v[i * 4 + 1] = u[c * 8 + i].y, v[i * 4 + 2] = u[c * 8 + i].z, v[i * 4 + 3] = u[c * 8 + i].w;
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 u = ld_shared_v4(sQst + c * 16384 + sw128_offset(r, i));
+                    v[i * 4 + 0] = u.x, v[i * 4 + 1] = u.y, v[i * 4 + 2] = u.z, v[i * 4 + 3] = u.w;
+                }
                 tmem_st_32x32(lane_addr + TM_Q + c * 32, v);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_ready);
+            if (tr && threadIdx.x == 0) g_attn_trace[8002] = clock64();
         }
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < n_blocks; ++j) {
@@ -578,35 +591,47 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
             trace_evt(tr0, 4096 + 16 * j + 13);
         }
         // ---- epilogue: O / l -> bf16, LSE
+        if (tr && threadIdx.x == 0) g_attn_trace[8003] = clock64();
         mbar_wait(&o_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1);
         tc_fence_after();
         const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+        const bool tma_out = (p.S % 128) == 0;  // whole 128-row boxes: stage O in the (idle) K ring and TMA-store full lines
         __nv_bfloat16* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(lane_addr + TM_O + c * 32, v);
             tmem_ld_wait();
-            if (row_ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 o;
-                    o.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
-                    o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
-                    o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
-                    o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
-                    st_v4(orow + c * 32 + g * 8, o);
-                }
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+                o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+                o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+                o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+                if (tma_out) st_shared_v4(sK + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + g), o);
+                else if (row_ok) st_v4(orow + c * 32 + g * 8, o);
+            }
+        }
+        if (tma_out) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (threadIdx.x == 0) {
+                for (int c = 0; c < NSUB; ++c) tma_store_2d(&tmO, sK + c * 16384, h * static_cast<int>(p.o_head_stride) + c * 64, row_base + q0);
+                tma_store_commit();
+                tma_store_wait_read<0>();  // shared memory must outlive the bulk stores READING it; the writes drain on their own
             }
         }
         if (row_ok) p.lse[(static_cast<size_t>(b) * p.H + h) * p.S + q_idx] = (m_used + log2f(l)) * LN2_F;
         tc_fence_before();
+        if (tr && threadIdx.x == 0) g_attn_trace[8004] = clock64();
     }
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (tr && threadIdx.x == 0) g_attn_trace[8005] = clock64(), g_attn_trace[8007] = globaltimer_ns();
 }
 
 // =================================================================================================================
@@ -970,7 +995,7 @@ __global__ void __launch_bounds__(192, 1)
 attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP,
                       const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDQ,
-                      const __nv_bfloat16* __restrict__ qptr, int64_t q_row_stride, const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tmQ, const AttnParams p) {
     using L = Dq256Smem;
     constexpr int D = 256, BT = 64, NSUB = 4;
     constexpr uint32_t TM_DQ = 0, TM_S = 256, TM_DP = 320, TM_Q = 384;
@@ -992,7 +1017,8 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
     uint64_t* s_free = bars + 11;    // 1 (4 warp arrivals)
     uint64_t* a_ready = bars + 12;   // 1
     uint64_t* dq_done = bars + 13;   // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* q_full = bars + 14;    // 1: the Q tile has landed in its staging area (ring slots 2 and 3)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
@@ -1022,6 +1048,7 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
         mbar_init(s_free, 4);
         mbar_init(a_ready, 1);
         mbar_init(dq_done, 1);
+        mbar_init(q_full, 1);
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -1042,6 +1069,10 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
     if (warp == 4) {
         // ---------------------------------------------------------------- TMA producer
         if (elect_one()) {
+            // Q tile -> ring slots 2, 3 (tile 1's K / V slots) on its way to TMEM: full lines through TMA instead of per-thread rows
+            mbar_expect_tx(q_full, 65536);
+            for (int c = 0; c < NSUB; ++c) tma_load_2d(sKV + 2 * KV_BYTES + c * 16384, &tmQ, q_full, col0 + c * 64, row_base + r0);
+            bool q_moved = false;
             mbar_expect_tx(do_full, 65536);
             for (int c = 0; c < NSUB; ++c) tma_load_2d(sDO + c * 16384, &tmDO, do_full, col0_do + c * 64, row_base + r0);
             // K and V tiles are loaded in tile order each, but whichever of the two next slots comes free first is served first
@@ -1053,11 +1084,13 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
             uint32_t spins = 0;
             while (next_k < n_tiles || next_v < n_tiles) {
                 bool progressed = false;
+                if (!q_moved) q_moved = mbar_try_wait(q_ready, 0);
 #pragma unroll
                 for (int is_k = 1; is_k >= 0; --is_k) {
                     const int t = is_k ? next_k : next_v;
                     if (t >= n_tiles) continue;
                     const int slot = is_k ? kslot(t) : vslot(t);
+                    if (slot >= 2 && !q_moved) continue;  // still holds the Q tile
                     if (((uses >> (8 * slot)) & 0xff) != static_cast<uint32_t>((t >> 1) & 0xff)) continue;
                     if (!mbar_try_wait(&slot_empty[slot], ((t >> 1) & 1) ^ 1)) continue;
                     uses += 1u << (8 * slot);
@@ -1170,16 +1203,16 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
         const int S_ = p.S;
         const bool causal_ = p.causal != 0;
         {
-            // Q row -> TMEM (bf16 pairs, 128 columns). All 32 loads are issued before the first store: one HBM round trip.
-            const __nv_bfloat16* qrow = qptr + static_cast<size_t>(row_base + (row_ok ? r_idx : r0)) * q_row_stride + col0;
-            uint4 u[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) u[i] = row_ok ? ld_nc_v4(qrow + i * 8) : make_uint4(0, 0, 0, 0);
+            // Q row: staging tile (SWIZZLE_128B, 4 sub-tiles of 64 columns) -> registers -> TMEM (bf16 pairs, 128 columns)
+            mbar_wait(q_full, 0);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i * 4 + 0] = u[c * 8 + i].x, v[i * 4 + 1] = u[c * 8 + i].y, v[i * 4 + 2] = u[c * 8 + i].z, v[i * 4 + 3] = u[c * 8 + i].w;
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 u = ld_shared_v4(sKV + 2 * KV_BYTES + c * 16384 + sw128_offset(r, i));
+                    v[i * 4 + 0] = u.x, v[i * 4 + 1] = u.y, v[i * 4 + 2] = u.z, v[i * 4 + 3] = u.w;
+                }
                 tmem_st_32x32(lane_addr + TM_Q + c * 32, v);
             }
             tmem_st_wait();
@@ -1290,7 +1323,7 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
         if (threadIdx.x == 0) {
             for (int c = 0; c < NSUB; ++c) tma_store_2d(&tmDQ, sDO + c * 16384, col0 + c * 64, row_base + r0);
             tma_store_commit();
-            tma_store_wait_all<0>();  // shared memory must outlive the bulk stores reading it
+            tma_store_wait_read<0>();  // shared memory must outlive the bulk stores reading it
         }
         tc_fence_before();
     }
@@ -1341,7 +1374,7 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
     p.d_real = a->D;
     p.pad3d = padded_head(a) ? 1 : 0;
-    static const int tr = getenv("B200_ATTN_TRACE") ? 1 : 0;
+    static const int tr = getenv("B200_ATTN_TRACE") ? atoi(getenv("B200_ATTN_TRACE")) : 0;  // 1: first CTA, 2: a late CTA
     p.trace = tr;
     return p;
 }
@@ -1372,14 +1405,16 @@ static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
 static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
     using L = Fwd256Smem;
     static_assert(L::TOTAL <= 232448, "fwd256 smem budget");
-    CUtensorMap tk, tv;
+    CUtensorMap tq, tk, tv, to;
     int rc;
+    if ((rc = qkv_tmap(&tq, a->q, a, a->qkv_row_stride, a->qkv_head_stride, 128))) return rc;
     if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
     if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    if ((rc = qkv_tmap(&to, a->o, a, a->o_row_stride, a->o_head_stride, 128))) return rc;
     auto kern = attn_fwd256_kernel;
     if ((rc = set_smem(kern, L::TOTAL, "attention_fwd256"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(tk, tv, static_cast<const __nv_bfloat16*>(a->q), a->qkv_row_stride, make_params(a));
+    kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, to, make_params(a));
     return check_launch("attention_fwd256");
 }
 
@@ -1427,10 +1462,12 @@ static int launch_bwd_dq256(const b200_attn_args* a, cudaStream_t st) {
     if ((rc = make_tmap_bf16_2d(&tp, a->p_scratch, a->S, zs, a->S, 64, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(&tds, a->ds_scratch, a->S, zs, a->S, 64, 128))) return rc;
     if ((rc = qkv_tmap(&tdq, a->dq, a, a->dqkv_row_stride, a->dqkv_head_stride, 128))) return rc;
+    CUtensorMap tq;
+    if ((rc = qkv_tmap(&tq, a->q, a, a->qkv_row_stride, a->qkv_head_stride, 128))) return rc;
     auto kern = attn_bwd_dq256_kernel;
     if ((rc = set_smem(kern, L::TOTAL, "attention_bwd_dq256"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(tdo, tk, tv, tp, tds, tdq, static_cast<const __nv_bfloat16*>(a->q), a->qkv_row_stride, make_params(a));
+    kern<<<grid, 192, L::TOTAL, st>>>(tdo, tk, tv, tp, tds, tdq, tq, make_params(a));
     return check_launch("attention_bwd_dq256");
 }
 

@@ -25,7 +25,7 @@ def timeit(fn, iters=10):
 
 
 def main():
-    cases = [("pythia-1b", 16, 2048, 8, 256, True), ("pythia-410m", 16, 2048, 16, 64, True), ("pythia-1.4b", 8, 2048, 16, 128, True),
+    cases = [("pythia-1b", 16, 2048, 8, 256, True), ("1b-noncausal", 16, 2048, 8, 256, False), ("pythia-410m", 16, 2048, 16, 64, True), ("pythia-1.4b", 8, 2048, 16, 128, True),
              ("roberta-large", 64, 512, 16, 64, False)]
     only = sys.argv[1:] or None
     print(f"{'case':16s} {'fwd ms':>8s} {'fwd TF/s':>9s} {'bwd ms':>8s} {'bwd TF/s':>9s}   (FLOPs = useful: causal halves)")

@@ -23,3 +23,7 @@ t0 = buf[4096 + 8]
 for t in range(32):
     g = lambda i: (buf[4096 + 16 * t + i] - t0) if buf[4096 + 16 * t + i] else -1
     print(f"j={t:2d} MMA s_issue={g(0):7d} pv_issue={g(1):7d} | SM top={g(8):7d} s_full={g(9):7d} max_done={g(10):7d} pbuf_free={g(11):7d} exp_done={g(12):7d} p_ready={g(13):7d}")
+
+e = [buf[8000 + i] for i in range(8)]
+print("entry->setup", e[1] - e[0], "setup->q_ready", e[2] - e[1], "q_ready->loop_end", e[3] - e[2], "epilogue", e[4] - e[3], "exit", e[5] - e[4],
+      "total cycles", e[5] - e[0], "total ns", e[7] - e[6])
