@@ -93,7 +93,7 @@ struct FwdSmem {
     static constexpr uint32_t OFF_K = Q_BYTES;
     static constexpr uint32_t OFF_V = OFF_K + STAGES * KV_BYTES;
     static constexpr uint32_t OFF_P = OFF_V + STAGES * KV_BYTES;
-    static constexpr uint32_t OFF_BAR = OFF_P + P_BYTES;
+    static constexpr uint32_t OFF_BAR = OFF_P + 2 * P_BYTES;  // two P tiles: softmax of block j+1 fills one while P V_j reads the other
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -119,8 +119,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* kv_empty = v_full + STAGES;      // STAGES
     uint64_t* s_full = kv_empty + STAGES;      // 2
     uint64_t* p_ready = s_full + 2;            // 1
-    uint64_t* o_done = p_ready + 1;            // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+    uint64_t* o_done = p_ready + 1;            // 2: o_done[b] = the P V that read P buffer b has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
@@ -144,7 +144,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(&s_full[0], 1);
         mbar_init(&s_full[1], 1);
         mbar_init(p_ready, 4);
-        mbar_init(o_done, 1);
+        mbar_init(&o_done[0], 1);
+        mbar_init(&o_done[1], 1);
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -209,12 +210,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * L::KV_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BN / 16; ++kk) {
-                    const uint64_t ad = p_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                    const uint64_t ad = p_desc + static_cast<uint64_t>(((j & 1) * L::P_BYTES + (kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
                     const uint64_t bd = vd + static_cast<uint64_t>((kk * 2048) >> 4);
                     umma_ss(tmem + TM_O, ad, bd, idesc_o, (j | kk) != 0);
                 }
                 tc_commit(&kv_empty[s]);
-                tc_commit(o_done);
+                tc_commit(&o_done[j & 1]);
             }
         }
         __syncwarp();
@@ -251,10 +252,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int i = 1; i < BN; ++i) mx = fmaxf(mx, x[i]);
             const float m_new = fmaxf(m_used, mx);
             const bool need = m_new > m_used + 8.0f;
-            if (j > 0) {
-                mbar_wait(o_done, (j - 1) & 1);  // PV_{j-1} retired: O is stable and the P tile may be overwritten
+            // P buffer j & 1 was last read by P V_{j-2}
+            if (j >= 2) mbar_wait(&o_done[j & 1], ((j >> 1) - 1) & 1);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                // rescaling O races with an in-flight P V: wait for the latest one (rare: the max must grow by > 2^8)
+                mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, need)) {
+                {
                     const float alpha = need ? ex2(m_used - m_new) : 1.0f;
                     l *= alpha;
 #pragma unroll 1
@@ -280,7 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     e[i] = ex2(x[cc * 8 + i] - m_safe);
                     sum += e[i];
                 }
-                st_operand_chunk(sP, r, cc, make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
+                st_operand_chunk(sP + (j & 1) * L::P_BYTES, r, cc, make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
             }
             l += sum;
             fence_proxy_async_smem();
@@ -289,7 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (lane == 0) mbar_arrive(p_ready);
         }
         // ---- epilogue: O / l -> bf16, LSE
-        mbar_wait(o_done, (n_blocks - 1) & 1);
+        mbar_wait(&o_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1);
         tc_fence_after();
         const float inv_l = l > 0.f ? 1.0f / l : 0.f;
         const bool row_ok = q_idx < p.S;
@@ -675,15 +679,20 @@ struct BwdSmem {
     static constexpr uint32_t OFF_R2 = R_BYTES;
     static constexpr uint32_t OFF_T1 = 2 * R_BYTES;
     static constexpr uint32_t OFF_T2 = OFF_T1 + STAGES * T_BYTES;
-    static constexpr uint32_t OFF_A1 = OFF_T2 + STAGES * T_BYTES;
-    static constexpr uint32_t OFF_A2 = OFF_A1 + 16384;
-    static constexpr uint32_t OFF_STAT = OFF_A2 + (DKV ? 16384 : 0);
-    static constexpr uint32_t OFF_BAR = OFF_STAT + (DKV ? 512 : 0);
+    static constexpr int ABUF = (D == 256 && DKV) ? 1 : 2;                 // operand tiles are double-buffered where they fit
+    static constexpr uint32_t OFF_A1 = OFF_T2 + STAGES * T_BYTES;          // dS (dQ pass) / P^T (dK/dV pass) tiles
+    static constexpr uint32_t OFF_A2 = OFF_A1 + ABUF * 16384;              // dS^T tiles (dK/dV pass only)
+    static constexpr uint32_t OFF_STAT = OFF_A2 + (DKV ? ABUF * 16384 : 0);  // [2][2][64] fp32 -lse*log2e, delta of the q tile
+    static constexpr uint32_t OFF_BAR = OFF_STAT + (DKV ? 1024 : 0);
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
 // DKV=false: resident R1=Q_i, R2=dO_i ; streamed T1=K_j, T2=V_j ; out dQ (all D columns).
 // DKV=true : resident R1=K_j, R2=V_j  ; streamed T1=Q_i, T2=dO_i; out dV, dK columns [half*DH, half*DH+DH).
+// Pipeline (same scheme as the head_dim-256 score pass): the score accumulators S / dP are double-buffered in TMEM and the
+// score MMAs of tile t+1 are issued as soon as their operands have landed and the compute warps have pulled tile t-1 out of
+// that buffer, so tensor work of tile t+1 overlaps the exp / multiply work of tile t; the bf16 operand tiles the compute
+// warps produce are double-buffered too; the issuer polls and serves whichever MMA group is ready.
 template <int D, int DH, int STAGES, bool DKV>
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
@@ -691,9 +700,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     using L = BwdSmem<D, STAGES, DKV>;
     constexpr int NSUB = L::NSUB;
     constexpr int BT = 64;
-    constexpr uint32_t TM_S = 0, TM_DP = 64, TM_ACC1 = 128, TM_ACC2 = 128 + DH;
-    static_assert(128 + (DKV ? 2 * DH : D) <= 512, "TMEM overflow");
+    constexpr uint32_t TM_ACC1 = 256, TM_ACC2 = 256 + DH;  // score buffers: S at b * 128, dP at b * 128 + 64 (b = tile & 1)
+    static_assert(256 + (DKV ? 2 * DH : D) <= 512, "TMEM overflow");
     constexpr int NSPLIT = D / DH;
+    constexpr int ABUF = L::ABUF;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -703,15 +713,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     uint8_t* sT2 = smem + L::OFF_T2;
     uint8_t* sA1 = smem + L::OFF_A1;
     uint8_t* sA2 = smem + L::OFF_A2;
-    float* sStat = reinterpret_cast<float*>(smem + L::OFF_STAT);  // DKV: [2][64] lse*log2e, delta of the streamed q tile
+    float* sStat = reinterpret_cast<float*>(smem + L::OFF_STAT);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* r_full = bars;                  // 1
     uint64_t* t_full = bars + 1;              // STAGES
     uint64_t* t_empty = t_full + STAGES;      // STAGES
-    uint64_t* s_full = t_empty + STAGES;      // 1
-    uint64_t* a_ready = s_full + 1;           // 1
-    uint64_t* acc_done = a_ready + 1;         // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+    uint64_t* s_full = t_empty + STAGES;      // 2
+    uint64_t* s_free = s_full + 2;            // 2 (4 warp arrivals)
+    uint64_t* a_ready = s_free + 2;           // 2 (4 warp arrivals)
+    uint64_t* acc_done = a_ready + 2;         // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 2);
+    static_assert((1 + 2 * STAGES + 8) * 8 + 4 <= 256, "barrier block overflow");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int blk = DKV ? (blockIdx.x / NSPLIT) : (gridDim.x - 1 - blockIdx.x);
@@ -721,7 +733,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     const int col0 = h * static_cast<int>(p.qkv_head_stride);
     const int col0_do = h * static_cast<int>(p.o_head_stride);  // dO shares O's layout, not the packed qkv layout
     const int row_base = b * p.S;
-    // streamed tile range
     int t_begin, t_end;
     if (!DKV) {
         t_begin = 0;
@@ -742,9 +753,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             mbar_init(&t_full[s], 1);
             mbar_init(&t_empty[s], 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(a_ready, 4);
-        mbar_init(acc_done, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_free[s], 4);
+            mbar_init(&a_ready[s], 4);
+            mbar_init(&acc_done[s], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 5) {
@@ -777,7 +791,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 5) {
-        // ---------------------------------------------------------------- MMA issuer (one elected thread)
+        // ---------------------------------------------------------------- MMA issuer (one elected thread, polling)
         if (elect_one()) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
             constexpr uint32_t idesc_acc = umma_idesc_bf16(128, DKV ? DH : D, false, true);
@@ -787,52 +801,67 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             const uint64_t t2k_desc0 = umma_desc_sw128(smem_u32(sT2), 16, 1024);
             const uint64_t t1m_desc0 = umma_desc_sw128(smem_u32(sT1), 8192, 1024);  // ... and as MN-major B (accumulate)
             const uint64_t t2m_desc0 = umma_desc_sw128(smem_u32(sT2), 8192, 1024);
-            const uint64_t a1_desc = umma_desc_sw128(smem_u32(sA1), 16, 1024);
-            const uint64_t a2_desc = umma_desc_sw128(smem_u32(sA2), 16, 1024);
+            const uint64_t a1_desc0 = umma_desc_sw128(smem_u32(sA1), 16, 1024);
+            const uint64_t a2_desc0 = umma_desc_sw128(smem_u32(sA2), 16, 1024);
             auto issue_scores = [&](int t) {
-                const int s = t % STAGES;
-                mbar_wait(&t_full[s], (t / STAGES) & 1);
-                tc_fence_after();
-                const uint64_t soff = static_cast<uint64_t>((s * L::T_BYTES) >> 4);
+                const uint64_t soff = static_cast<uint64_t>(((t % STAGES) * L::T_BYTES) >> 4);
+                const uint32_t tb = tmem + (t & 1) * 128;
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint64_t ad = r1_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
-                    const uint64_t bd = t1k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4);
-                    umma_ss(tmem + TM_S, ad, bd, idesc_s, kk != 0);
-                }
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tb, r1_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                            t1k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
 #pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint64_t ad = r2_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
-                    const uint64_t bd = t2k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4);
-                    umma_ss(tmem + TM_DP, ad, bd, idesc_s, kk != 0);
-                }
-                tc_commit(s_full);
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tb + 64, r2_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                            t2k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
+                tc_commit(&s_full[t & 1]);
             };
-            mbar_wait(r_full, 0);
-            if (n_tiles > 0) issue_scores(0);
-            for (int t = 0; t < n_tiles; ++t) {
+            auto issue_acc = [&](int t) {
                 const int s = t % STAGES;
-                mbar_wait(a_ready, t & 1);
-                tc_fence_after();
                 const uint64_t soff = static_cast<uint64_t>((s * L::T_BYTES) >> 4);
                 const uint64_t boff = soff + static_cast<uint64_t>((half * (DH / 64) * 8192) >> 4);  // this CTA's output half
+                const uint64_t aoff = static_cast<uint64_t>(((t % ABUF) * 16384) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < BT / 16; ++kk) {
                     if (!DKV) {
                         // dQ += dS (K-major A) * K_j (MN-major B)
-                        umma_ss(tmem + TM_ACC1, a1_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                        umma_ss(tmem + TM_ACC1, a1_desc0 + aoff + static_cast<uint64_t>((kk * 32) >> 4),
                                 t1m_desc0 + soff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
                     } else {
                         // dV += P^T * dO_i ; dK += dS^T * Q_i
-                        umma_ss(tmem + TM_ACC1, a1_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                        umma_ss(tmem + TM_ACC1, a1_desc0 + aoff + static_cast<uint64_t>((kk * 32) >> 4),
                                 t2m_desc0 + boff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
-                        umma_ss(tmem + TM_ACC2, a2_desc + static_cast<uint64_t>((kk * 32) >> 4),
+                        umma_ss(tmem + TM_ACC2, a2_desc0 + aoff + static_cast<uint64_t>((kk * 32) >> 4),
                                 t1m_desc0 + boff + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
                     }
                 }
                 tc_commit(&t_empty[s]);
-                tc_commit(acc_done);
-                if (t + 1 < n_tiles) issue_scores(t + 1);
+                tc_commit(&acc_done[t % ABUF]);
+            };
+            mbar_wait(r_full, 0);
+            tc_fence_after();
+            int next_sc = 0, next_acc = 0;
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_acc < n_tiles) {
+                bool progressed = false;
+                // scores of tile t: operands landed, and (t >= 2) the compute warps have pulled tile t-2 out of this buffer
+                if (next_sc < n_tiles && next_sc < next_acc + 2 && mbar_try_wait(&t_full[next_sc % STAGES], (next_sc / STAGES) & 1) &&
+                    (next_sc < 2 || mbar_try_wait(&s_free[next_sc & 1], ((next_sc >> 1) - 1) & 1))) {
+                    tc_fence_after();
+                    issue_scores(next_sc);
+                    ++next_sc, progressed = true;
+                }
+                if (next_acc < next_sc && mbar_try_wait(&a_ready[next_acc % ABUF], (next_acc / ABUF) & 1)) {
+                    tc_fence_after();
+                    issue_acc(next_acc);
+                    ++next_acc, progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention bwd issuer stalled (block %d,%d,%d sc %d acc %d of %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                           next_sc, next_acc, n_tiles);
+                    __trap();
+                }
             }
         }
         __syncwarp();
@@ -840,78 +869,94 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         // ---------------------------------------------------------------- compute warps: thread = resident row
         const int r = warp * 32 + lane;
         const int r_idx = r0 + r;
+        const bool row_ok = r_idx < p.S;
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         const float sl2 = p.scale * LOG2E_F;
         const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.S;
-        float my_lse2 = 0.f, my_delta = 0.f;
-        if (!DKV && r_idx < p.S) {
-            my_lse2 = p.lse[stat_base + r_idx] * LOG2E_F;
+        // dQ pass: this row's statistics; a row beyond S gets lse = +inf so that every P (and dS) of it is exactly 0
+        float neg_lse2 = -INFINITY, my_delta = 0.f;
+        if (!DKV && row_ok) {
+            neg_lse2 = -p.lse[stat_base + r_idx] * LOG2E_F;
             my_delta = p.delta[stat_base + r_idx];
         }
         for (int t = 0; t < n_tiles; ++t) {
             const int c0 = (t_begin + t) * BT;  // first streamed row (kv for dQ, q for dK/dV)
+            float* st = sStat + (t & 1) * 128;
             if (DKV) {
-                // stage the streamed q tile's statistics; previous iteration's readers are past a_ready -> s_full chain
-                named_bar_sync(1, 128);
+                // statistics of the streamed q tile -> smem buffer t & 1 (last read two tiles ago: everyone is past the
+                // named barrier of tile t-1 by now)
                 if (r < BT) {
                     const int qi = c0 + r;
-                    sStat[r] = qi < p.S ? p.lse[stat_base + qi] * LOG2E_F : 0.f;
-                    sStat[64 + r] = qi < p.S ? p.delta[stat_base + qi] : 0.f;
+                    st[r] = qi < p.S ? -p.lse[stat_base + qi] * LOG2E_F : -INFINITY;
+                    st[64 + r] = qi < p.S ? p.delta[stat_base + qi] : 0.f;
                 }
                 named_bar_sync(1, 128);
             }
-            mbar_wait(s_full, t & 1);
+            mbar_wait(&s_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
             uint32_t sv[64], dv[64];
-            tmem_ld_32x32(lane_addr + TM_S, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-            tmem_ld_32x32(lane_addr + TM_S + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-            tmem_ld_32x32(lane_addr + TM_DP, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
-            tmem_ld_32x32(lane_addr + TM_DP + 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
+            const uint32_t tb = lane_addr + (t & 1) * 128;
+            tmem_ld_32x32(tb, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x32(tb + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+            tmem_ld_32x32(tb + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
+            tmem_ld_32x32(tb + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
             tmem_ld_wait();
-            // s_full of tile t implies every earlier MMA (incl. the accumulate MMAs of tile t-1) retired: A tiles are free
-#pragma unroll
-            for (int cc = 0; cc < BT / 8; ++cc) {
-                float pv[8], ds[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = cc * 8 + i;
-                    const int c_idx = c0 + c;
-                    bool keep = (c_idx < p.S) && (r_idx < p.S);
-                    float lse2, dlt;
-                    if (!DKV) {
-                        if (p.causal && c_idx > r_idx) keep = false;  // key after query
-                        lse2 = my_lse2, dlt = my_delta;
-                    } else {
-                        if (p.causal && c_idx < r_idx) keep = false;  // query before key
-                        lse2 = sStat[c], dlt = sStat[64 + c];
-                    }
-                    const float pe = keep ? ex2(__uint_as_float(sv[c]) * sl2 - lse2) : 0.f;
-                    pv[i] = pe;
-                    ds[i] = pe * (__uint_as_float(dv[c]) - dlt);
-                }
-                const uint4 dsv = make_uint4(f2_to_bf2(ds[0], ds[1]), f2_to_bf2(ds[2], ds[3]), f2_to_bf2(ds[4], ds[5]), f2_to_bf2(ds[6], ds[7]));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[t & 1]);
+            // masking is branch-free inside the tile (score -> -inf => P = dS = 0) and skipped for interior tiles
+            bool need_mask;
+            if (!DKV) need_mask = (c0 + BT > p.S) || (p.causal && c0 + BT - 1 > r0);
+            else need_mask = (c0 + BT > p.S) || !row_ok || (p.causal && c0 < r0 + 127);
+            if (need_mask) {
                 if (!DKV) {
-                    st_operand_chunk(sA1, r, cc, dsv);
-                    if (p.p_out != nullptr && r_idx < p.S) {
-                        // thread = query row: 16 B of P and of dS per chunk, 128 contiguous bytes per row and tile
+                    const int lim = p.causal ? min(p.S - 1, r_idx) : p.S - 1;  // last visible key of this query row
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) sv[i] = (c0 + i > lim) ? 0xff800000u : sv[i];
+                } else {
+                    const int first = (p.causal ? r_idx : 0);                  // first query that sees this key row
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) sv[i] = (!row_ok || c0 + i < first || c0 + i >= p.S) ? 0xff800000u : sv[i];
+                }
+            }
+            uint32_t pk[32], dk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float l0, l1, d0, d1;
+                if (!DKV) l0 = l1 = neg_lse2, d0 = d1 = my_delta;
+                else l0 = st[2 * i], l1 = st[2 * i + 1], d0 = st[64 + 2 * i], d1 = st[64 + 2 * i + 1];
+                const float pe0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, l0));
+                const float pe1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, l1));
+                pk[i] = f2_to_bf2(pe0, pe1);
+                dk[i] = f2_to_bf2(pe0 * (__uint_as_float(dv[2 * i]) - d0), pe1 * (__uint_as_float(dv[2 * i + 1]) - d1));
+            }
+            // operand buffer t % ABUF was last read by the accumulate MMAs of tile t - ABUF
+            if (t >= ABUF) mbar_wait(&acc_done[t % ABUF], ((t / ABUF) - 1) & 1);
+            uint8_t* a1 = sA1 + (t % ABUF) * 16384;
+            uint8_t* a2 = sA2 + (t % ABUF) * 16384;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                const uint4 pvec = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+                const uint4 dvec = make_uint4(dk[cc * 4], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
+                if (!DKV) {
+                    st_shared_v4(a1 + sw128_offset(r, cc), dvec);
+                    if (p.p_out != nullptr && row_ok) {
                         const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + c0 + cc * 8;
-                        st_v4(p.p_out + off, make_uint4(f2_to_bf2(pv[0], pv[1]), f2_to_bf2(pv[2], pv[3]), f2_to_bf2(pv[4], pv[5]), f2_to_bf2(pv[6], pv[7])));
-                        st_v4(p.ds_out + off, dsv);
+                        st_v4(p.p_out + off, pvec);
+                        st_v4(p.ds_out + off, dvec);
                     }
                 } else {
-                    st_operand_chunk(sA1, r, cc, make_uint4(f2_to_bf2(pv[0], pv[1]), f2_to_bf2(pv[2], pv[3]), f2_to_bf2(pv[4], pv[5]), f2_to_bf2(pv[6], pv[7])));
-                    st_operand_chunk(sA2, r, cc, dsv);
+                    st_shared_v4(a1 + sw128_offset(r, cc), pvec);
+                    st_shared_v4(a2 + sw128_offset(r, cc), dvec);
                 }
             }
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready);
+            if (lane == 0) mbar_arrive(&a_ready[t % ABUF]);
         }
         if (!DKV && p.p_out != nullptr && p.causal && (blk & 1) == 0 && r_idx < p.S && r0 + 128 < p.S) {
-            // The batched dK/dV GEMMs work on 256-key tiles and start their reduction at the tile's first query row, so
-            // for the first 128 queries of such a tile they also read keys [r0+128, r0+256): never visited by this
-            // causal pass -> must hold zeros.
+            // (score-scratch mode of this generic kernel, kept for triage: see attn_bwd_dq256_kernel)
             const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + r0 + 128;
             const int n = min(128, p.S - (r0 + 128));
             for (int c = 0; c < n; c += 8) {
@@ -921,10 +966,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         }
         // ---- epilogue
         if (n_tiles > 0) {
-            mbar_wait(acc_done, (n_tiles - 1) & 1);
+            mbar_wait(&acc_done[(n_tiles - 1) % ABUF], ((n_tiles - 1) / ABUF) & 1);
             tc_fence_after();
         }
-        const bool row_ok = r_idx < p.S;
         constexpr int NOUT = DKV ? 2 : 1;
 #pragma unroll 1
         for (int which = 0; which < NOUT; ++which) {
@@ -1518,7 +1562,7 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
     cudaStream_t st = as_stream(stream);
     switch (a->D) {
         // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
-        case 64: return launch_fwd<64, 128, 5>(a, st);
+        case 64: return launch_fwd<64, 128, 4>(a, st);
         case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: {
@@ -1548,12 +1592,12 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
     }
     switch (a->D) {
         case 64:
-            if ((rc = launch_bwd<64, 64, 8, false>(a, st))) return rc;
-            return launch_bwd<64, 64, 8, true>(a, st);
+            if ((rc = launch_bwd<64, 64, 6, false>(a, st))) return rc;
+            return launch_bwd<64, 64, 6, true>(a, st);
         case 80:
         case 128:
             if ((rc = launch_bwd<128, 128, 4, false>(a, st))) return rc;
-            return launch_bwd<128, 128, 4, true>(a, st);
+            return launch_bwd<128, 128, 3, true>(a, st);
         default:
             if (score_path) {
                 // head_dim 256: the dQ pass also writes its P / dS tiles; dK and dV become batched causal GEMMs (5 matmul
