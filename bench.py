@@ -197,6 +197,8 @@ def main_b200(a):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     strategy = a.strategy or ("none" if world == 1 else "zero1")
 

@@ -742,6 +742,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         t_end = (p.S + BT - 1) / BT;
     }
     const int n_tiles = t_end - t_begin;
+    const bool tr = p.trace == 3 && DKV && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1 && threadIdx.x == 0;
+    if (tr) g_attn_trace[8100] = clock64(), g_attn_trace[8108] = globaltimer_ns();
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmR1);
@@ -769,6 +771,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (tr) g_attn_trace[8101] = clock64();
 
     if (warp == 4) {
         // ---------------------------------------------------------------- TMA producer (one elected thread)
@@ -879,21 +882,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             neg_lse2 = -p.lse[stat_base + r_idx] * LOG2E_F;
             my_delta = p.delta[stat_base + r_idx];
         }
+        // dK/dV pass: statistics (-lse*log2e, delta) of the streamed q tile go through smem buffer t & 1. They are fetched one
+        // tile ahead into registers (threads r < 64) so that their global-load latency overlaps the previous tile's math:
+        // loading them at the top of each iteration stalled all 128 threads for a full memory round trip per tile.
+        float nx_l = -INFINITY, nx_d = 0.f;
+        auto fetch_stats = [&](int t) {
+            const int qi = (t_begin + t) * BT + r;
+            nx_l = qi < p.S ? -p.lse[stat_base + qi] * LOG2E_F : -INFINITY;
+            nx_d = qi < p.S ? p.delta[stat_base + qi] : 0.f;
+        };
+        if (DKV && r < BT && n_tiles > 0) {
+            fetch_stats(0);
+            sStat[r] = nx_l, sStat[64 + r] = nx_d;
+        }
         for (int t = 0; t < n_tiles; ++t) {
             const int c0 = (t_begin + t) * BT;  // first streamed row (kv for dQ, q for dK/dV)
             float* st = sStat + (t & 1) * 128;
             if (DKV) {
-                // statistics of the streamed q tile -> smem buffer t & 1 (last read two tiles ago: everyone is past the
-                // named barrier of tile t-1 by now)
-                if (r < BT) {
-                    const int qi = c0 + r;
-                    st[r] = qi < p.S ? -p.lse[stat_base + qi] * LOG2E_F : -INFINITY;
-                    st[64 + r] = qi < p.S ? p.delta[stat_base + qi] : 0.f;
-                }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 128);  // buffer t & 1 (written at the end of the previous iteration) is visible
+                if (r < BT && t + 1 < n_tiles) fetch_stats(t + 1);
             }
             mbar_wait(&s_full[t & 1], (t >> 1) & 1);
             tc_fence_after();
+            if (tr && t == 0) g_attn_trace[8102] = clock64();
+            if (tr && t == 1) g_attn_trace[8103] = clock64();
             uint32_t sv[64], dv[64];
             const uint32_t tb = lane_addr + (t & 1) * 128;
             tmem_ld_32x32(tb, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -921,14 +933,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             }
             uint32_t pk[32], dk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float l0, l1, d0, d1;
-                if (!DKV) l0 = l1 = neg_lse2, d0 = d1 = my_delta;
-                else l0 = st[2 * i], l1 = st[2 * i + 1], d0 = st[64 + 2 * i], d1 = st[64 + 2 * i + 1];
-                const float pe0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, l0));
-                const float pe1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, l1));
-                pk[i] = f2_to_bf2(pe0, pe1);
-                dk[i] = f2_to_bf2(pe0 * (__uint_as_float(dv[2 * i]) - d0), pe1 * (__uint_as_float(dv[2 * i + 1]) - d1));
+            for (int q4 = 0; q4 < 16; ++q4) {  // 4 score columns per step; the dK/dV pass reads their statistics as float4
+                float4 l4 = make_float4(neg_lse2, neg_lse2, neg_lse2, neg_lse2), d4 = make_float4(my_delta, my_delta, my_delta, my_delta);
+                if (DKV) {
+                    l4 = reinterpret_cast<const float4*>(st)[q4];
+                    d4 = reinterpret_cast<const float4*>(st + 64)[q4];
+                }
+                const float pe0 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 0]), sl2, l4.x));
+                const float pe1 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 1]), sl2, l4.y));
+                const float pe2 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 2]), sl2, l4.z));
+                const float pe3 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 3]), sl2, l4.w));
+                pk[2 * q4] = f2_to_bf2(pe0, pe1);
+                pk[2 * q4 + 1] = f2_to_bf2(pe2, pe3);
+                dk[2 * q4] = f2_to_bf2(pe0 * (__uint_as_float(dv[4 * q4 + 0]) - d4.x), pe1 * (__uint_as_float(dv[4 * q4 + 1]) - d4.y));
+                dk[2 * q4 + 1] = f2_to_bf2(pe2 * (__uint_as_float(dv[4 * q4 + 2]) - d4.z), pe3 * (__uint_as_float(dv[4 * q4 + 3]) - d4.w));
             }
             // operand buffer t % ABUF was last read by the accumulate MMAs of tile t - ABUF
             if (t >= ABUF) mbar_wait(&acc_done[t % ABUF], ((t / ABUF) - 1) & 1);
@@ -954,6 +972,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[t % ABUF]);
+            if (DKV && r < BT && t + 1 < n_tiles) {
+                // buffer (t+1) & 1 was last read in iteration t-1; everyone has passed this iteration's barrier since
+                float* nst = sStat + ((t + 1) & 1) * 128;
+                nst[r] = nx_l, nst[64 + r] = nx_d;
+            }
         }
         if (!DKV && p.p_out != nullptr && p.causal && (blk & 1) == 0 && r_idx < p.S && r0 + 128 < p.S) {
             // (score-scratch mode of this generic kernel, kept for triage: see attn_bwd_dq256_kernel)
@@ -965,10 +988,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             }
         }
         // ---- epilogue
+        if (tr) g_attn_trace[8104] = clock64();
         if (n_tiles > 0) {
             mbar_wait(&acc_done[(n_tiles - 1) % ABUF], ((n_tiles - 1) / ABUF) & 1);
             tc_fence_after();
         }
+        if (tr) g_attn_trace[8105] = clock64();
         constexpr int NOUT = DKV ? 2 : 1;
 #pragma unroll 1
         for (int which = 0; which < NOUT; ++which) {
@@ -1005,12 +1030,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             }
         }
         tc_fence_before();
+        if (tr) g_attn_trace[8106] = clock64();
     }
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (tr) g_attn_trace[8107] = clock64(), g_attn_trace[8109] = globaltimer_ns();
 }
 
 // =================================================================================================================
