@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 6
+#define B200PT_ABI_VERSION 7
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
@@ -165,6 +165,11 @@ typedef struct b200_attn_args {
      * ever writes the lower block triangle; the buffers need no initialisation. */
     void* p_scratch;
     void* ds_scratch;
+    /* attention-probability dropout (RoBERTa: nn.Dropout on the softmax output, HF:models/roberta/modeling_roberta.py:209,236).
+     * The mask is a pure function of (dropout_seed, b*H+h, query, key); forward and backward must be given the same
+     * (dropout_p, dropout_seed). 0 = off. p is quantised to 1/65536. */
+    float dropout_p;
+    uint64_t dropout_seed;
 } b200_attn_args;
 int b200_attention_fwd(const b200_attn_args* args, b200_stream_t stream);
 int b200_attention_bwd(const b200_attn_args* args, b200_stream_t stream);

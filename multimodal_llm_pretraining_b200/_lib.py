@@ -14,7 +14,7 @@ import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libb200pt.so"
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -46,6 +46,7 @@ class AttnArgs(C.Structure):
         ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("dqkv_row_stride", c_int64), ("dqkv_head_stride", c_int64),
         ("p_scratch", c_void_p), ("ds_scratch", c_void_p),
+        ("dropout_p", c_float), ("dropout_seed", C.c_uint64),
     ]
 
 

@@ -61,11 +61,36 @@ struct AttnParams {
     int64_t dqkv_row_stride, dqkv_head_stride;
     __nv_bfloat16* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
     int trace;
+    // attention-probability dropout (RoBERTa, HF:models/roberta/modeling_roberta.py:209,236): keep iff hash16 >= drop_thr,
+    // kept probabilities scaled by drop_scale = 65536 / (65536 - drop_thr); 0 = off. Generic kernels only.
+    uint32_t drop_thr;
+    float drop_scale;
+    unsigned long long drop_seed;
     const __nv_bfloat16* d_o;  // score pass: delta = rowsum(dO * O) is computed in its prologue (no separate pre-pass)
     int d_real;  // head_dim as stored (80 for Pythia-2.8b); the kernels run on D = d_real rounded up to 64/128/256 with the
     int pad3d;   // tail columns zero-filled by 3-D TMA maps {d, head, token} (pad3d = 1) and clipped again on store
     __nv_bfloat16* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
 };
+
+// Dropout mask of score element (q, k) of head bh: the 16-bit lane (q & 1) * 2 + (k & 1) of one 64-bit hash per 2 x 2 block of
+// the [S, S] score matrix. Forward (thread = query row, walks keys) and both backward passes (thread = query or key row)
+// recompute the same bits; a 2 x 2 grouping costs half a hash per element whichever way a thread walks.
+__device__ __forceinline__ uint64_t attn_mix64(uint64_t x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ uint64_t attn_drop_hash(unsigned long long seed, int bh, int S, int q, int k) {
+    const uint64_t half = static_cast<uint64_t>((S + 1) >> 1);
+    const uint64_t blk = (static_cast<uint64_t>(bh) * half + static_cast<uint64_t>(q >> 1)) * half + static_cast<uint64_t>(k >> 1);
+    return attn_mix64(seed + 0x9e3779b97f4a7c15ull * (blk + 1));
+}
+__device__ __forceinline__ bool attn_drop_keep(uint64_t hsh, int q, int k, uint32_t thr) {
+    return ((static_cast<uint32_t>(hsh >> (16 * (((q & 1) << 1) | (k & 1))))) & 0xffffu) >= thr;
+}
 
 // 64-column box c of head h, rows [row, row + box_rows): 2-D map {row width, tokens} or, for padded head dims, 3-D map
 // {d, head, token} whose out-of-extent columns arrive as zeros
@@ -282,7 +307,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     e[i] = ex2(x[cc * 8 + i] - m_safe);
-                    sum += e[i];
+                    sum += e[i];  // the softmax denominator is taken before dropout
+                }
+                if (p.drop_thr) {
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        const int kv = kv0 + cc * 8 + 2 * i2;
+                        const uint64_t hsh = attn_drop_hash(p.drop_seed, b * p.H + h, p.S, q_idx, kv);
+                        e[2 * i2] = attn_drop_keep(hsh, q_idx, kv, p.drop_thr) ? e[2 * i2] * p.drop_scale : 0.f;
+                        e[2 * i2 + 1] = attn_drop_keep(hsh, q_idx, kv + 1, p.drop_thr) ? e[2 * i2 + 1] * p.drop_scale : 0.f;
+                    }
                 }
                 st_operand_chunk(sP + (j & 1) * L::P_BYTES, r, cc, make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
             }
@@ -943,10 +977,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 const float pe1 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 1]), sl2, l4.y));
                 const float pe2 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 2]), sl2, l4.z));
                 const float pe3 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 3]), sl2, l4.w));
-                pk[2 * q4] = f2_to_bf2(pe0, pe1);
-                pk[2 * q4 + 1] = f2_to_bf2(pe2, pe3);
-                dk[2 * q4] = f2_to_bf2(pe0 * (__uint_as_float(dv[4 * q4 + 0]) - d4.x), pe1 * (__uint_as_float(dv[4 * q4 + 1]) - d4.y));
-                dk[2 * q4 + 1] = f2_to_bf2(pe2 * (__uint_as_float(dv[4 * q4 + 2]) - d4.z), pe3 * (__uint_as_float(dv[4 * q4 + 3]) - d4.w));
+                float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;  // dropout mask / keep probability
+                if (p.drop_thr) {
+                    const int cq = c0 + 4 * q4;  // streamed index of the first of the 4 elements
+                    const int bh = b * p.H + h;
+                    // (query, key) of element e: dQ pass (r_idx, cq + e); dK/dV pass (cq + e, r_idx)
+                    const uint64_t ha = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq);
+                    const uint64_t hb = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq + 2, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq + 2);
+                    auto keep = [&](uint64_t hsh, int e) { return DKV ? attn_drop_keep(hsh, cq + e, r_idx, p.drop_thr) : attn_drop_keep(hsh, r_idx, cq + e, p.drop_thr); };
+                    m0 = keep(ha, 0) ? p.drop_scale : 0.f;
+                    m1 = keep(ha, 1) ? p.drop_scale : 0.f;
+                    m2 = keep(hb, 2) ? p.drop_scale : 0.f;
+                    m3 = keep(hb, 3) ? p.drop_scale : 0.f;
+                }
+                // P^T operand of dV carries the mask; dS = P * (mask * dP - delta)
+                pk[2 * q4] = f2_to_bf2(pe0 * m0, pe1 * m1);
+                pk[2 * q4 + 1] = f2_to_bf2(pe2 * m2, pe3 * m3);
+                dk[2 * q4] = f2_to_bf2(pe0 * (__uint_as_float(dv[4 * q4 + 0]) * m0 - d4.x), pe1 * (__uint_as_float(dv[4 * q4 + 1]) * m1 - d4.y));
+                dk[2 * q4 + 1] = f2_to_bf2(pe2 * (__uint_as_float(dv[4 * q4 + 2]) * m2 - d4.z), pe3 * (__uint_as_float(dv[4 * q4 + 3]) * m3 - d4.w));
             }
             // operand buffer t % ABUF was last read by the accumulate MMAs of tile t - ABUF
             if (t >= ABUF) mbar_wait(&acc_done[t % ABUF], ((t / ABUF) - 1) & 1);
@@ -1412,6 +1460,7 @@ static int check_common(const b200_attn_args* a, const char* who) {
     B200_REQUIRE(a != nullptr, "%s: null args", who);
     B200_REQUIRE(a->D == 64 || a->D == 80 || a->D == 128 || a->D == 256, "%s: head_dim %d unsupported (64, 80, 128, 256)", who, a->D);
     B200_REQUIRE(a->B > 0 && a->S > 0 && a->H > 0, "%s: bad B/S/H", who);
+    B200_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "%s: dropout_p must be in [0, 1)", who);
     B200_REQUIRE(a->qkv_row_stride % 8 == 0 && a->qkv_head_stride % 8 == 0, "%s: q/k/v strides must be multiples of 8 elements", who);
     B200_REQUIRE(a->o_row_stride % 8 == 0 && a->o_head_stride % 8 == 0 && aligned16(a->o), "%s: o must be 16B aligned with strides %% 8 == 0", who);
     B200_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v), "%s: q/k/v must be 16B aligned", who);
@@ -1442,6 +1491,9 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.dv = static_cast<__nv_bfloat16*>(a->dv);
     p.dqkv_row_stride = a->dqkv_row_stride, p.dqkv_head_stride = a->dqkv_head_stride;
     p.p_out = nullptr, p.ds_out = nullptr;
+    p.drop_thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr);
+    p.drop_seed = a->dropout_seed;
     p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
     p.d_real = a->D;
     p.pad3d = padded_head(a) ? 1 : 0;
@@ -1594,7 +1646,7 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: {
             static const bool old_fwd = getenv("B200_ATTN_OLD_FWD") != nullptr;  // perf triage only
-            return old_fwd ? launch_fwd<256, 64, 2>(a, st) : launch_fwd256(a, st);
+            return (old_fwd || a->dropout_p > 0.f) ? launch_fwd<256, 64, 2>(a, st) : launch_fwd256(a, st);
         }
     }
 }
@@ -1607,7 +1659,7 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
                  "attention_bwd: gradient buffers must be 16B aligned with strides %% 8 == 0");
     cudaStream_t st = as_stream(stream);
     static const bool old_dq = getenv("B200_ATTN_OLD_DQ") != nullptr;  // perf triage only
-    const bool score_path = a->D == 256 && a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0;
+    const bool score_path = a->D == 256 && a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0 && a->dropout_p == 0.f;
     {
         const int64_t total_warps = static_cast<int64_t>(a->B) * a->S * a->H;
         int64_t blocks = (total_warps + 7) / 8;

@@ -278,23 +278,27 @@ def _score_scratch(device, Z: int, S: int):
     return _score_cache[key]
 
 
-def attention_fwd(q, k, v, causal, scale=None):
-    """q,k,v: bf16 views [B,S,H,D] (any token/head strides, e.g. slices of a packed qkv buffer). Returns (o [B,S,H,D], lse [B,H,S])."""
+def attention_fwd(q, k, v, causal, scale=None, dropout_p: float = 0.0, dropout_seed: int = 0):
+    """q,k,v: bf16 views [B,S,H,D] (any token/head strides, e.g. slices of a packed qkv buffer). Returns (o [B,S,H,D], lse [B,H,S]).
+    dropout_p > 0 drops softmax probabilities with the counter-based mask of (dropout_seed, head, query, key)."""
     B, S, H, D = q.shape
     scale = D ** -0.5 if scale is None else scale
     o = torch.empty(B, S, H, D, dtype=BF16, device=q.device)
     lse = torch.empty(B, H, S, dtype=F32, device=q.device)
     a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
+    a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     check(_L(q).b200_attention_fwd(C.byref(a), stream_ptr()), "b200_attention_fwd")
     _count(1)
     return o, lse
 
 
-def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None):
-    """dq,dk,dv: bf16 views [B,S,H,D] sharing strides (e.g. slices of a packed dqkv buffer); written, not accumulated."""
+def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None, dropout_p: float = 0.0, dropout_seed: int = 0):
+    """dq,dk,dv: bf16 views [B,S,H,D] sharing strides (e.g. slices of a packed dqkv buffer); written, not accumulated.
+    (dropout_p, dropout_seed) must be the forward's."""
     B, S, H, D = q.shape
     scale = D ** -0.5 if scale is None else scale
     a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
+    a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
     _req(d_o.dtype == BF16 and d_o.shape == o.shape and d_o.stride() == o.stride(), "attention_bwd: dO must match O")
     for t in (dq, dk, dv):
         _req(t.dtype == BF16 and t.shape == (B, S, H, D) and t.stride(3) == 1 and t.stride(0) == S * t.stride(1), "attention_bwd: bad dq/dk/dv")
@@ -302,7 +306,7 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None):
     delta = torch.empty(B, H, S, dtype=F32, device=q.device)
     a.d_o, a.delta = ptr(d_o), ptr(delta)
     n_launch = 3
-    if D == 256 and S % 256 == 0 and USE_SCORE_SCRATCH:
+    if D == 256 and S % 256 == 0 and USE_SCORE_SCRATCH and dropout_p == 0.0:
         # head_dim 256: P / dS tiles go through HBM scratch and dK / dV become batched GEMMs (b200pt.h, b200_attn_args)
         ps, dss = _score_scratch(q.device, B * H, S)
         a.p_scratch, a.ds_scratch = ptr(ps), ptr(dss)

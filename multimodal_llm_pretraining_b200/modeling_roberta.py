@@ -10,10 +10,9 @@ bias+residual, LayerNorm, in-place cross entropy over all positions.
 Layout notes
   * V = 50265 is odd: the word-embedding / decoder matrix and the decoder bias are allocated with zero padding to 50304 rows
     (FlatParams alloc_shape) so that logits rows are 16-byte aligned; the padding is never updated and never scored.
-  * Dropout (hidden 0.1, attention-probability 0.1 in roberta-large): hidden dropout is a counter-based mask recomputed in
-    backward (b200_dropout); p = 0 is the parity configuration. Attention-probability dropout is not built: the module
-    refuses attention_probs_dropout_prob > 0 in training mode unless `allow_missing_attention_dropout=True` is passed by
-    the caller (timing runs) — stated in DESIGN.md.
+  * Dropout (hidden 0.1, attention-probability 0.1 in roberta-large): both are counter-based masks recomputed in backward
+    (b200_dropout for hidden states; inside the flash-attention kernels for the softmax probabilities). p = 0 is the
+    bit-comparable parity configuration; with p > 0 parity is checked against a reference that applies the same masks.
 """
 
 from __future__ import annotations
@@ -244,7 +243,8 @@ class B200RobertaForMaskedLM(_FlatModule):
         drop = train and self.p_hidden > 0.0
         qkv = K.gemm(x, self._qkv_w(p), bias=self._qkv_b(p, self.flat.master))  # [T, 3h] = q | k | v
         q4 = qkv.view(B, S, 3, nh, hd)
-        o, lse = K.attention_fwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=False, scale=hd ** -0.5)
+        pa = self.p_attn if train else 0.0
+        o, lse = K.attention_fwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=False, scale=hd ** -0.5, dropout_p=pa, dropout_seed=self._seed(4 * i + 3))
         o2 = o.view(B * S, h)
         wo, bo = self._w(f"{p}.attention.output.dense.weight"), self._p(f"{p}.attention.output.dense.bias")
         if drop:
@@ -288,7 +288,8 @@ class B200RobertaForMaskedLM(_FlatModule):
         dqkv = torch.empty_like(qkv)
         q4, d4 = qkv.view(B, S, 3, nh, hd), dqkv.view(B, S, 3, nh, hd)
         K.attention_bwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], o, lse, d_o.view(B, S, nh, hd),
-                        d4[:, :, 0], d4[:, :, 1], d4[:, :, 2], causal=False, scale=hd ** -0.5)
+                        d4[:, :, 0], d4[:, :, 1], d4[:, :, 2], causal=False, scale=hd ** -0.5,
+                        dropout_p=self.p_attn if train else 0.0, dropout_seed=self._seed(4 * i + 3))
         K.gemm(dqkv, x, a_mn=True, b_mn=True, out=self._qkv_gw(p), accumulate=True)
         K.colsum_(dqkv, self._qkv_b(p, self.flat.grad))
         return K.gemm(dqkv, self._qkv_w(p), b_mn=True, residual=ds1)  # + residual branch of s1
@@ -384,9 +385,6 @@ class B200RobertaForMaskedLM(_FlatModule):
         ids = input_ids.to(self.device).contiguous()
         B, S = ids.shape
         train = torch.is_grad_enabled() and self.training
-        if train and self.p_attn > 0.0 and not self.allow_missing_attention_dropout:
-            raise NotImplementedError("attention-probability dropout is not built: set attention_probs_dropout_prob=0 "
-                                      "or pass allow_missing_attention_dropout=True (see DESIGN.md)")
         if labels is not None and train:
             if self._grads_were_dropped():
                 self.zero_grad()

@@ -129,3 +129,56 @@ def test_attention_bwd_d256_scratch_paths_agree_and_ignore_stale_scratch(dev, us
     for name, got, ref in (("dQ", dq, qf.grad), ("dK", dk, kf.grad), ("dV", dv, vf.grad)):
         assert torch.isfinite(got.float()).all(), f"{name} has non-finite values"
         assert rel_err(got, ref) <= 2e-2, f"{name} rel err {rel_err(got, ref):.3e}"
+
+
+def _drop_keep_mask(seed, B, H, S, p):
+    """Host restatement of the kernels' counter-based mask (attention.cu attn_drop_hash / attn_drop_keep): one splitmix64
+    hash per 2 x 2 block of each head's [S, S] score matrix, 16-bit lane (q & 1) * 2 + (k & 1) compared with round(p * 65536)."""
+    import numpy as np
+
+    thr = np.uint64(int(p * 65536.0 + 0.5))
+    half = np.uint64((S + 1) // 2)
+    bh = np.arange(B * H, dtype=np.uint64)[:, None, None]
+    q = np.arange(S, dtype=np.uint64)[None, :, None]
+    k = np.arange(S, dtype=np.uint64)[None, None, :]
+    with np.errstate(over="ignore"):
+        blk = (bh * half + (q >> np.uint64(1))) * half + (k >> np.uint64(1))
+        x = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (blk + np.uint64(1))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+        lane = ((q & np.uint64(1)) << np.uint64(1)) | (k & np.uint64(1))
+        bits = (x >> (np.uint64(16) * lane)) & np.uint64(0xFFFF)
+    keep = bits >= thr
+    return torch.from_numpy(keep.reshape(B, H, S, S)), 65536.0 / (65536.0 - float(thr))
+
+
+@pytest.mark.parametrize("B,S,H,D,causal", [(2, 256, 2, 64, False), (1, 384, 2, 64, True), (1, 256, 2, 128, False), (1, 256, 1, 256, True)])
+def test_attention_dropout_matches_reference_with_same_mask(dev, B, S, H, D, causal):
+    """Softmax-probability dropout: forward output and all three gradients against an fp32 reference that applies the SAME
+    mask (reconstructed on the host from the counter-based rule); keep rate statistics."""
+    p_drop, seed = 0.1, 0x1234ABCD5678
+    _, q, k, v = make_qkv(B, S, H, D, True, dev, seed=S + D + 1)
+    scale = D ** -0.5
+    keep, inv_keep = _drop_keep_mask(seed, B, H, S, p_drop)
+    assert abs(keep.float().mean().item() - (1 - p_drop)) < 5e-3
+    keep = keep.to(dev)
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    qh, kh, vh = (t.permute(0, 2, 1, 3) for t in (qf, kf, vf))
+    sc = (qh @ kh.transpose(-1, -2)) * scale
+    if causal:
+        sc = sc.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=dev).tril(), float("-inf"))
+    pr = torch.softmax(sc, dim=-1) * keep * inv_keep
+    ro = (pr @ vh).permute(0, 2, 1, 3)
+    o, lse = K.attention_fwd(q, k, v, causal, scale, dropout_p=p_drop, dropout_seed=seed)
+    assert rel_err(o, ro) <= 2e-2, rel_err(o, ro)
+    d_o = torch.randn(B, S, H, D, generator=torch.Generator(device="cpu").manual_seed(9)).to(dev).to(BF16)
+    ro.backward(d_o.float())
+    dbuf = torch.full((B, S, H, 3, D), float("nan"), device=dev, dtype=BF16)
+    dq, dk, dv = dbuf[:, :, :, 0], dbuf[:, :, :, 1], dbuf[:, :, :, 2]
+    K.attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale, dropout_p=p_drop, dropout_seed=seed)
+    for name, got, ref in (("dQ", dq, qf.grad), ("dK", dk, kf.grad), ("dV", dv, vf.grad)):
+        assert torch.isfinite(got.float()).all(), name
+        assert rel_err(got, ref) <= 2e-2, (name, rel_err(got, ref))

@@ -159,8 +159,20 @@ def test_training_with_hidden_dropout_runs_and_learns(gold, dev):
     assert torch.isfinite(torch.tensor(last)) and last < 0.7 * first, (first, last)
 
 
-def test_attention_dropout_is_refused_loudly(gold, dev):
-    m = build(gold, dev, attention_probs_dropout_prob=0.1)
+def test_training_with_attention_dropout_runs_and_learns(gold, dev):
+    m = build(gold, dev, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    opt = B200Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.98))
     b = gold["batches"][0].to(dev)
-    with pytest.raises(NotImplementedError):
-        m(input_ids=b, labels=b)
+    first = last = None
+    for _ in range(30):
+        loss = m(input_ids=b, labels=b)["loss"]
+        loss.backward()
+        opt.step()
+        m.zero_grad()
+        first = loss.item() if first is None else first
+        last = loss.item()
+    assert torch.isfinite(torch.tensor(last)) and last < 0.7 * first, (first, last)
+    # eval mode applies no dropout: deterministic
+    m.eval()
+    a = m(input_ids=b, labels=b)["loss"].item()
+    assert a == m(input_ids=b, labels=b)["loss"].item()
