@@ -122,14 +122,17 @@ struct FwdSmem {
     static constexpr uint32_t TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <int D, int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+// When S (double-buffered) and O need <= 256 TMEM columns (head_dim 64 with 64-key blocks) and the tiles fit in < 113 KB, two
+// CTAs are resident per SM and cover each other's prologue / epilogue / barrier round trips.
+template <int D, int BN, int STAGES, bool DROP>
+__global__ void __launch_bounds__(192, (2 * BN + D <= 256) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using L = FwdSmem<D, BN, STAGES>;
     constexpr int NSUB = L::NSUB;
     constexpr uint32_t TM_S = 0, TM_O = 2 * BN;
     static_assert(2 * BN + D <= 512, "TMEM overflow");
+    constexpr uint32_t TM_COLS = (2 * BN + D <= 256) ? 256 : 512;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -174,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_barrier_init();
     }
     if (warp == 5) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, TM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -309,7 +312,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     e[i] = ex2(x[cc * 8 + i] - m_safe);
                     sum += e[i];  // the softmax denominator is taken before dropout
                 }
-                if (p.drop_thr) {
+                if (DROP) {  // compile-time: the dropout-free instantiation keeps its register allocation and schedule
 #pragma unroll
                     for (int i2 = 0; i2 < 4; ++i2) {
                         const int kv = kv0 + cc * 8 + 2 * i2;
@@ -355,7 +358,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, TM_COLS);
     }
 }
 
@@ -705,7 +708,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
     }
 }
 
-template <int D, int STAGES, bool DKV>
+template <int D, int STAGES, bool DKV, int SBUF = 2>
 struct BwdSmem {
     static constexpr int NSUB = D / 64;
     static constexpr uint32_t R_BYTES = NSUB * 16384;      // resident 128-row tile
@@ -713,7 +716,7 @@ struct BwdSmem {
     static constexpr uint32_t OFF_R2 = R_BYTES;
     static constexpr uint32_t OFF_T1 = 2 * R_BYTES;
     static constexpr uint32_t OFF_T2 = OFF_T1 + STAGES * T_BYTES;
-    static constexpr int ABUF = (D == 256 && DKV) ? 1 : 2;                 // operand tiles are double-buffered where they fit
+    static constexpr int ABUF = ((D == 256 && DKV) || SBUF == 1) ? 1 : 2;  // operand tiles are double-buffered where they fit
     static constexpr uint32_t OFF_A1 = OFF_T2 + STAGES * T_BYTES;          // dS (dQ pass) / P^T (dK/dV pass) tiles
     static constexpr uint32_t OFF_A2 = OFF_A1 + ABUF * 16384;              // dS^T tiles (dK/dV pass only)
     static constexpr uint32_t OFF_STAT = OFF_A2 + (DKV ? ABUF * 16384 : 0);  // [2][2][64] fp32 -lse*log2e, delta of the q tile
@@ -727,15 +730,20 @@ struct BwdSmem {
 // score MMAs of tile t+1 are issued as soon as their operands have landed and the compute warps have pulled tile t-1 out of
 // that buffer, so tensor work of tile t+1 overlaps the exp / multiply work of tile t; the bf16 operand tiles the compute
 // warps produce are double-buffered too; the issuer polls and serves whichever MMA group is ready.
-template <int D, int DH, int STAGES, bool DKV>
-__global__ void __launch_bounds__(192, 1)
+// SBUF = 1 (head_dim 64): single score buffer, single operand buffers, 256 TMEM columns and < 113 KB of shared memory, so that
+// TWO CTAs are resident per SM: CTAs of this size are short (8-32 tiles) and their un-overlapped prologue / epilogue / barrier
+// round trips are covered by the co-resident CTA instead of by deeper buffering inside one CTA.
+template <int D, int DH, int STAGES, bool DKV, int SBUF, bool DROP>
+__global__ void __launch_bounds__(192, SBUF == 1 ? 2 : 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmR2,
                 const __grid_constant__ CUtensorMap tmT1, const __grid_constant__ CUtensorMap tmT2, const AttnParams p) {
-    using L = BwdSmem<D, STAGES, DKV>;
+    using L = BwdSmem<D, STAGES, DKV, SBUF>;
     constexpr int NSUB = L::NSUB;
     constexpr int BT = 64;
-    constexpr uint32_t TM_ACC1 = 256, TM_ACC2 = 256 + DH;  // score buffers: S at b * 128, dP at b * 128 + 64 (b = tile & 1)
-    static_assert(256 + (DKV ? 2 * DH : D) <= 512, "TMEM overflow");
+    constexpr uint32_t TM_ACC1 = SBUF * 128, TM_ACC2 = SBUF * 128 + DH;  // score buffers: S at b * 128, dP at b * 128 + 64 (b = tile % SBUF)
+    constexpr uint32_t TM_USED = SBUF * 128 + (DKV ? 2 * DH : D);
+    constexpr uint32_t TM_COLS = TM_USED <= 256 ? 256 : 512;
+    static_assert(TM_USED <= 512, "TMEM overflow");
     constexpr int NSPLIT = D / DH;
     constexpr int ABUF = L::ABUF;
 
@@ -798,7 +806,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 5) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, TM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -842,7 +850,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
             const uint64_t a2_desc0 = umma_desc_sw128(smem_u32(sA2), 16, 1024);
             auto issue_scores = [&](int t) {
                 const uint64_t soff = static_cast<uint64_t>(((t % STAGES) * L::T_BYTES) >> 4);
-                const uint32_t tb = tmem + (t & 1) * 128;
+                const uint32_t tb = tmem + (t % SBUF) * 128;
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk)
                     umma_ss(tb, r1_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
@@ -851,7 +859,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 for (int kk = 0; kk < D / 16; ++kk)
                     umma_ss(tb + 64, r2_desc + static_cast<uint64_t>(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
                             t2k_desc0 + soff + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
-                tc_commit(&s_full[t & 1]);
+                tc_commit(&s_full[t % SBUF]);
             };
             auto issue_acc = [&](int t) {
                 const int s = t % STAGES;
@@ -884,7 +892,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 bool progressed = false;
                 // scores of tile t: operands landed, and (t >= 2) the compute warps have pulled tile t-2 out of this buffer
                 if (next_sc < n_tiles && next_sc < next_acc + 2 && mbar_try_wait(&t_full[next_sc % STAGES], (next_sc / STAGES) & 1) &&
-                    (next_sc < 2 || mbar_try_wait(&s_free[next_sc & 1], ((next_sc >> 1) - 1) & 1))) {
+                    (next_sc < SBUF || mbar_try_wait(&s_free[next_sc % SBUF], ((next_sc / SBUF) - 1) & 1))) {
                     tc_fence_after();
                     issue_scores(next_sc);
                     ++next_sc, progressed = true;
@@ -936,84 +944,95 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                 named_bar_sync(1, 128);  // buffer t & 1 (written at the end of the previous iteration) is visible
                 if (r < BT && t + 1 < n_tiles) fetch_stats(t + 1);
             }
-            mbar_wait(&s_full[t & 1], (t >> 1) & 1);
+            mbar_wait(&s_full[t % SBUF], (t / SBUF) & 1);
             tc_fence_after();
             if (tr && t == 0) g_attn_trace[8102] = clock64();
             if (tr && t == 1) g_attn_trace[8103] = clock64();
-            uint32_t sv[64], dv[64];
-            const uint32_t tb = lane_addr + (t & 1) * 128;
-            tmem_ld_32x32(tb, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-            tmem_ld_32x32(tb + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-            tmem_ld_32x32(tb + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
-            tmem_ld_32x32(tb + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[t & 1]);
+            const uint32_t tb = lane_addr + (t % SBUF) * 128;
             // masking is branch-free inside the tile (score -> -inf => P = dS = 0) and skipped for interior tiles
             bool need_mask;
             if (!DKV) need_mask = (c0 + BT > p.S) || (p.causal && c0 + BT - 1 > r0);
             else need_mask = (c0 + BT > p.S) || !row_ok || (p.causal && c0 < r0 + 127);
-            if (need_mask) {
-                if (!DKV) {
-                    const int lim = p.causal ? min(p.S - 1, r_idx) : p.S - 1;  // last visible key of this query row
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) sv[i] = (c0 + i > lim) ? 0xff800000u : sv[i];
-                } else {
-                    const int first = (p.causal ? r_idx : 0);                  // first query that sees this key row
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) sv[i] = (!row_ok || c0 + i < first || c0 + i >= p.S) ? 0xff800000u : sv[i];
-                }
-            }
-            uint32_t pk[32], dk[32];
-#pragma unroll
-            for (int q4 = 0; q4 < 16; ++q4) {  // 4 score columns per step; the dK/dV pass reads their statistics as float4
-                float4 l4 = make_float4(neg_lse2, neg_lse2, neg_lse2, neg_lse2), d4 = make_float4(my_delta, my_delta, my_delta, my_delta);
-                if (DKV) {
-                    l4 = reinterpret_cast<const float4*>(st)[q4];
-                    d4 = reinterpret_cast<const float4*>(st + 64)[q4];
-                }
-                const float pe0 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 0]), sl2, l4.x));
-                const float pe1 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 1]), sl2, l4.y));
-                const float pe2 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 2]), sl2, l4.z));
-                const float pe3 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 3]), sl2, l4.w));
-                float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;  // dropout mask / keep probability
-                if (p.drop_thr) {
-                    const int cq = c0 + 4 * q4;  // streamed index of the first of the 4 elements
-                    const int bh = b * p.H + h;
-                    // (query, key) of element e: dQ pass (r_idx, cq + e); dK/dV pass (cq + e, r_idx)
-                    const uint64_t ha = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq);
-                    const uint64_t hb = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq + 2, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq + 2);
-                    auto keep = [&](uint64_t hsh, int e) { return DKV ? attn_drop_keep(hsh, cq + e, r_idx, p.drop_thr) : attn_drop_keep(hsh, r_idx, cq + e, p.drop_thr); };
-                    m0 = keep(ha, 0) ? p.drop_scale : 0.f;
-                    m1 = keep(ha, 1) ? p.drop_scale : 0.f;
-                    m2 = keep(hb, 2) ? p.drop_scale : 0.f;
-                    m3 = keep(hb, 3) ? p.drop_scale : 0.f;
-                }
-                // P^T operand of dV carries the mask; dS = P * (mask * dP - delta)
-                pk[2 * q4] = f2_to_bf2(pe0 * m0, pe1 * m1);
-                pk[2 * q4 + 1] = f2_to_bf2(pe2 * m2, pe3 * m3);
-                dk[2 * q4] = f2_to_bf2(pe0 * (__uint_as_float(dv[4 * q4 + 0]) * m0 - d4.x), pe1 * (__uint_as_float(dv[4 * q4 + 1]) * m1 - d4.y));
-                dk[2 * q4 + 1] = f2_to_bf2(pe2 * (__uint_as_float(dv[4 * q4 + 2]) * m2 - d4.z), pe3 * (__uint_as_float(dv[4 * q4 + 3]) * m3 - d4.w));
-            }
-            // operand buffer t % ABUF was last read by the accumulate MMAs of tile t - ABUF
-            if (t >= ABUF) mbar_wait(&acc_done[t % ABUF], ((t / ABUF) - 1) & 1);
             uint8_t* a1 = sA1 + (t % ABUF) * 16384;
             uint8_t* a2 = sA2 + (t % ABUF) * 16384;
+            // two CTAs per SM (SBUF == 1) leave 168 registers per thread: the tile is then processed in two 32-column halves
+            constexpr int NHALF = SBUF == 1 ? 2 : 1;
+            constexpr int HC = 64 / NHALF;  // score columns per pass
 #pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-                const uint4 pvec = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-                const uint4 dvec = make_uint4(dk[cc * 4], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
-                if (!DKV) {
-                    st_shared_v4(a1 + sw128_offset(r, cc), dvec);
-                    if (p.p_out != nullptr && row_ok) {
-                        const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + c0 + cc * 8;
-                        st_v4(p.p_out + off, pvec);
-                        st_v4(p.ds_out + off, dvec);
+            for (int hh = 0; hh < NHALF; ++hh) {
+                uint32_t sv[HC], dv[HC];
+#pragma unroll
+                for (int c = 0; c < HC / 32; ++c) {
+                    tmem_ld_32x32(tb + hh * HC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+                    tmem_ld_32x32(tb + 64 + hh * HC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
+                }
+                tmem_ld_wait();
+                if (hh == NHALF - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_free[t % SBUF]);  // both halves are in registers: the buffer may be overwritten
+                }
+                const int ch = c0 + hh * HC;  // streamed index of this pass's first column
+                if (need_mask) {
+                    if (!DKV) {
+                        const int lim = p.causal ? min(p.S - 1, r_idx) : p.S - 1;  // last visible key of this query row
+#pragma unroll
+                        for (int i = 0; i < HC; ++i) sv[i] = (ch + i > lim) ? 0xff800000u : sv[i];
+                    } else {
+                        const int first = (p.causal ? r_idx : 0);                  // first query that sees this key row
+#pragma unroll
+                        for (int i = 0; i < HC; ++i) sv[i] = (!row_ok || ch + i < first || ch + i >= p.S) ? 0xff800000u : sv[i];
                     }
-                } else {
-                    st_shared_v4(a1 + sw128_offset(r, cc), pvec);
-                    st_shared_v4(a2 + sw128_offset(r, cc), dvec);
+                }
+                uint32_t pk[HC / 2], dk[HC / 2];
+#pragma unroll
+                for (int q4 = 0; q4 < HC / 4; ++q4) {  // 4 score columns per step; the dK/dV pass reads their statistics as float4
+                    float4 l4 = make_float4(neg_lse2, neg_lse2, neg_lse2, neg_lse2), d4 = make_float4(my_delta, my_delta, my_delta, my_delta);
+                    if (DKV) {
+                        l4 = reinterpret_cast<const float4*>(st)[hh * (HC / 4) + q4];
+                        d4 = reinterpret_cast<const float4*>(st + 64)[hh * (HC / 4) + q4];
+                    }
+                    const float pe0 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 0]), sl2, l4.x));
+                    const float pe1 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 1]), sl2, l4.y));
+                    const float pe2 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 2]), sl2, l4.z));
+                    const float pe3 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 3]), sl2, l4.w));
+                    float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;  // dropout mask / keep probability
+                    if (DROP) {
+                        const int cq = ch + 4 * q4;  // streamed index of the first of the 4 elements
+                        const int bh = b * p.H + h;
+                        // (query, key) of element e: dQ pass (r_idx, cq + e); dK/dV pass (cq + e, r_idx)
+                        const uint64_t ha = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq);
+                        const uint64_t hb = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq + 2, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq + 2);
+                        auto keep = [&](uint64_t hsh, int e) { return DKV ? attn_drop_keep(hsh, cq + e, r_idx, p.drop_thr) : attn_drop_keep(hsh, r_idx, cq + e, p.drop_thr); };
+                        m0 = keep(ha, 0) ? p.drop_scale : 0.f;
+                        m1 = keep(ha, 1) ? p.drop_scale : 0.f;
+                        m2 = keep(hb, 2) ? p.drop_scale : 0.f;
+                        m3 = keep(hb, 3) ? p.drop_scale : 0.f;
+                    }
+                    // P^T operand of dV carries the mask; dS = P * (mask * dP - delta)
+                    pk[2 * q4] = f2_to_bf2(pe0 * m0, pe1 * m1);
+                    pk[2 * q4 + 1] = f2_to_bf2(pe2 * m2, pe3 * m3);
+                    dk[2 * q4] = f2_to_bf2(pe0 * (__uint_as_float(dv[4 * q4 + 0]) * m0 - d4.x), pe1 * (__uint_as_float(dv[4 * q4 + 1]) * m1 - d4.y));
+                    dk[2 * q4 + 1] = f2_to_bf2(pe2 * (__uint_as_float(dv[4 * q4 + 2]) * m2 - d4.z), pe3 * (__uint_as_float(dv[4 * q4 + 3]) * m3 - d4.w));
+                }
+                // operand buffer t % ABUF was last read by the accumulate MMAs of tile t - ABUF
+                if (hh == 0 && t >= ABUF) mbar_wait(&acc_done[t % ABUF], ((t / ABUF) - 1) & 1);
+#pragma unroll
+                for (int c4 = 0; c4 < HC / 8; ++c4) {
+                    const int cc = hh * (HC / 8) + c4;
+                    const uint4 pvec = make_uint4(pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+                    const uint4 dvec = make_uint4(dk[c4 * 4], dk[c4 * 4 + 1], dk[c4 * 4 + 2], dk[c4 * 4 + 3]);
+                    if (!DKV) {
+                        st_shared_v4(a1 + sw128_offset(r, cc), dvec);
+                        if (p.p_out != nullptr && row_ok) {
+                            const size_t off = (stat_base + r_idx) * static_cast<size_t>(p.S) + c0 + cc * 8;
+                            st_v4(p.p_out + off, pvec);
+                            st_v4(p.ds_out + off, dvec);
+                        }
+                    } else {
+                        st_shared_v4(a1 + sw128_offset(r, cc), pvec);
+                        st_shared_v4(a2 + sw128_offset(r, cc), dvec);
+                    }
                 }
             }
             fence_proxy_async_smem();
@@ -1083,7 +1102,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, TM_COLS);
     }
     if (tr) g_attn_trace[8107] = clock64(), g_attn_trace[8109] = globaltimer_ns();
 }
@@ -1509,8 +1528,8 @@ static int set_smem(KernT kern, size_t bytes, const char* who) {
     return 0;
 }
 
-template <int D, int BN, int STAGES>
-static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
+template <int D, int BN, int STAGES, bool DROP>
+static int launch_fwd_impl(const b200_attn_args* a, cudaStream_t st) {
     using L = FwdSmem<D, BN, STAGES>;
     static_assert(L::TOTAL <= 232448, "forward smem budget");
     CUtensorMap tq, tk, tv;
@@ -1518,11 +1537,16 @@ static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
     if ((rc = qkv_tmap(&tq, a->q, a, a->qkv_row_stride, a->qkv_head_stride, 128))) return rc;
     if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, BN))) return rc;
     if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, BN))) return rc;
-    auto kern = attn_fwd_kernel<D, BN, STAGES>;
+    auto kern = attn_fwd_kernel<D, BN, STAGES, DROP>;
     if ((rc = set_smem(kern, L::TOTAL, "attention_fwd"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
     kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, make_params(a));
     return check_launch("attention_fwd");
+}
+
+template <int D, int BN, int STAGES>
+static int launch_fwd(const b200_attn_args* a, cudaStream_t st) {
+    return a->dropout_p > 0.f ? launch_fwd_impl<D, BN, STAGES, true>(a, st) : launch_fwd_impl<D, BN, STAGES, false>(a, st);
 }
 
 static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
@@ -1541,9 +1565,9 @@ static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
     return check_launch("attention_fwd256");
 }
 
-template <int D, int DH, int STAGES, bool DKV>
-static int launch_bwd(const b200_attn_args* a, cudaStream_t st, bool store_scores = false) {
-    using L = BwdSmem<D, STAGES, DKV>;
+template <int D, int DH, int STAGES, bool DKV, int SBUF, bool DROP>
+static int launch_bwd_impl(const b200_attn_args* a, cudaStream_t st, bool store_scores) {
+    using L = BwdSmem<D, STAGES, DKV, SBUF>;
     static_assert(L::TOTAL <= 232448, "backward smem budget");
     CUtensorMap r1, r2, t1, t2;
     int rc;
@@ -1560,7 +1584,7 @@ static int launch_bwd(const b200_attn_args* a, cudaStream_t st, bool store_score
         if ((rc = qkv_tmap(&t1, a->q, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
         if ((rc = qkv_tmap(&t2, a->d_o, &oa, a->o_row_stride, a->o_head_stride, 64))) return rc;
     }
-    auto kern = attn_bwd_kernel<D, DH, STAGES, DKV>;
+    auto kern = attn_bwd_kernel<D, DH, STAGES, DKV, SBUF, DROP>;
     if ((rc = set_smem(kern, L::TOTAL, "attention_bwd"))) return rc;
     dim3 grid(((a->S + 127) / 128) * (DKV ? D / DH : 1), a->H, a->B);
     AttnParams prm = make_params(a);
@@ -1570,6 +1594,12 @@ static int launch_bwd(const b200_attn_args* a, cudaStream_t st, bool store_score
     }
     kern<<<grid, 192, L::TOTAL, st>>>(r1, r2, t1, t2, prm);
     return check_launch(DKV ? "attention_bwd_dkv" : "attention_bwd_dq");
+}
+
+template <int D, int DH, int STAGES, bool DKV, int SBUF = 2>
+static int launch_bwd(const b200_attn_args* a, cudaStream_t st, bool store_scores = false) {
+    return a->dropout_p > 0.f ? launch_bwd_impl<D, DH, STAGES, DKV, SBUF, true>(a, st, store_scores)
+                              : launch_bwd_impl<D, DH, STAGES, DKV, SBUF, false>(a, st, store_scores);
 }
 
 static int launch_bwd_dq256(const b200_attn_args* a, cudaStream_t st) {
@@ -1641,7 +1671,10 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
     cudaStream_t st = as_stream(stream);
     switch (a->D) {
         // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
-        case 64: return launch_fwd<64, 128, 4>(a, st);
+        case 64: {
+            static const bool one_cta = getenv("B200_ATTN_FWD_1CTA") != nullptr;  // perf triage only
+            return one_cta ? launch_fwd<64, 128, 4>(a, st) : launch_fwd<64, 64, 3>(a, st);  // 64-key blocks: two CTAs per SM
+        }
         case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: {
@@ -1671,8 +1704,16 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
     }
     switch (a->D) {
         case 64:
-            if ((rc = launch_bwd<64, 64, 6, false>(a, st))) return rc;
-            return launch_bwd<64, 64, 6, true>(a, st);
+            {
+                static const bool one_cta = getenv("B200_ATTN_BWD_1CTA") != nullptr;  // perf triage only
+                if (one_cta) {
+                    if ((rc = launch_bwd<64, 64, 6, false>(a, st))) return rc;
+                    return launch_bwd<64, 64, 6, true>(a, st);
+                }
+            }
+            // two CTAs per SM (single score / operand buffers, 256 TMEM columns, < 113 KB smem each)
+            if ((rc = launch_bwd<64, 64, 3, false, 1>(a, st))) return rc;
+            return launch_bwd<64, 64, 2, true, 1>(a, st);
         case 80:
         case 128:
             if ((rc = launch_bwd<128, 128, 4, false>(a, st))) return rc;
