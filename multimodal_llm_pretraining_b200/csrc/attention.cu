@@ -1673,7 +1673,11 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
         case 64: {
             static const bool one_cta = getenv("B200_ATTN_FWD_1CTA") != nullptr;  // perf triage only
-            return one_cta ? launch_fwd<64, 128, 4>(a, st) : launch_fwd<64, 64, 3>(a, st);  // 64-key blocks: two CTAs per SM
+            // 64-key blocks, two CTAs per SM. The dropout instantiation of that variant faulted intermittently inside a
+            // 24-layer model (not reproducible stand-alone, root cause not found): dropout runs use the one-CTA layout,
+            // which is covered by tests/test_roberta_gpu.py::test_full_depth_training_steps_with_dropout.
+            if (one_cta || a->dropout_p > 0.f) return launch_fwd<64, 128, 4>(a, st);
+            return launch_fwd<64, 64, 3>(a, st);
         }
         case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
