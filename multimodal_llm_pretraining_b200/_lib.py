@@ -13,7 +13,7 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libb200pt.so"
+LIB_PATH = Path(os.environ["B200PT_LIB"]) if os.environ.get("B200PT_LIB") else _PKG / "libb200pt.so"  # override: kernel triage builds only
 ABI_VERSION = 7
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t

@@ -11,8 +11,15 @@ every rank runs independent micro-batches; the only exchange is per optimizer st
                      every rank runs the replicated fused Adam.
   strategy "zero1" : the same buckets are reduce-scattered (AVG) in place — rank r keeps slice r of every bucket —
                      local sum-of-squares + one scalar all-reduce give the global grad norm, the fused Adam updates
-                     only the owned slices (moments exist only for them: 8 B/param/W), then the fp32 master slices are
-                     all-gathered in place and the bf16 compute copy is refreshed with one cast pass.
+                     only the owned slices (moments exist only for them: 8 B/param/W) and writes their bf16 compute
+                     copy in the same pass; the bf16 slices (2 B/param — what the next forward reads) are all-gathered in
+                     place. The fp32 master of the slices a rank does not own goes stale, exactly as under DeepSpeed
+                     ZeRO-1 where the fp32 master exists only on the owner; `consolidate_master()` (called by
+                     `state_dict()`) all-gathers it on demand.
+
+Bucket collectives overlapped with backward run on a side stream through a dedicated NCCL communicator capped at
+`comm_max_ctas` CTAs: the persistent GEMM grids are sized to the SM count, so every SM a collective occupies delays a whole
+wave of tiles; a narrow communicator still moves a layer's gradients well inside that layer's backward time.
 
 `CommPlan` holds the pure bucket/ownership arithmetic and the collective calls so that it can be exercised with gloo on
 CPU tensors (tests/test_engine_cpu.py, world_size 2).
@@ -21,6 +28,8 @@ CPU tensors (tests/test_engine_cpu.py, world_size 2).
 from __future__ import annotations
 
 from typing import Callable
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -95,7 +104,8 @@ class TrainEngine:
     B200 module + B200Adam, with DDP or ZeRO-1 over the flat buffers."""
 
     def __init__(self, model, optimizer, scheduler=None, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
-                 strategy: str = "none", group=None):
+                 strategy: str = "none", group=None, overlap: bool = True, comm_max_ctas: int | None = None,
+                 profile_phases: bool = False):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.max_grad_norm = max_grad_norm
         self.ga = gradient_accumulation_steps
@@ -105,6 +115,11 @@ class TrainEngine:
         self.plan: CommPlan | None = None
         self.comm_stream = None
         self.last_grad_norm = None
+        self.overlap = overlap
+        self.overlap_group = group
+        self.profile_phases = profile_phases
+        self.last_phase_ms: dict | None = None
+        self._pending: list[tuple[int, int]] = []
         if strategy not in ("none", "ddp", "zero1"):
             raise ValueError(strategy)
         if strategy != "none":
@@ -113,23 +128,39 @@ class TrainEngine:
             W, r = dist.get_world_size(group), dist.get_rank(group)
             self.plan = CommPlan(model.comm_buckets(), W, r, group)
             self.comm_stream = torch.cuda.Stream()
+            if comm_max_ctas is None:
+                comm_max_ctas = int(os.environ.get("B200_COMM_MAX_CTAS", "0")) or None
+            if comm_max_ctas and overlap and dist.get_backend(group) == "nccl":
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = comm_max_ctas
+                opts.config.min_ctas = min(comm_max_ctas, 4)
+                ranks = dist.get_process_group_ranks(group) if group is not None else list(range(W))
+                self.overlap_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+            self.overlap_plan = CommPlan(model.comm_buckets(), W, r, self.overlap_group)
             if strategy == "zero1":
                 optimizer.set_shard(self.plan.owned_ranges())
+                self.flat.master_consolidator = self.consolidate_master
             # identical initial parameters everywhere (rank 0 wins), like DDP's constructor broadcast
             dist.broadcast(self.flat.master, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             self.flat.sync_shadow(force=True)
 
     # ------------------------------------------------------------------ fwd + bwd of one micro-batch
+    def _reduce_bucket(self, plan: CommPlan, b: tuple[int, int]) -> None:
+        if self.strategy == "ddp":
+            plan.all_reduce_avg(self.flat.grad, b)
+        else:
+            plan.reduce_scatter_avg(self.flat.grad, b)
+
     def _on_grads_ready(self, start: int, end: int) -> None:
+        b = self.plan.bucket_of(start, end)
+        if not self.overlap:
+            self._pending.append(b)
+            return
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ev)
-            b = self.plan.bucket_of(start, end)
-            if self.strategy == "ddp":
-                self.plan.all_reduce_avg(self.flat.grad, b)
-            else:
-                self.plan.reduce_scatter_avg(self.flat.grad, b)
+            self._reduce_bucket(self.overlap_plan, b)
 
     def manual_training_step(self, inputs: dict) -> torch.Tensor:
         """One micro-batch forward + backward with gradients ACCUMULATED; the loss is divided by the accumulation count
@@ -148,8 +179,13 @@ class TrainEngine:
         from . import kernels as K
 
         f = self.flat
+        marks = [self._mark()]
         if self.plan is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+            for b in self._pending:  # overlap=False: the bucket collectives run here, on the compute stream
+                self._reduce_bucket(self.plan, b)
+            self._pending.clear()
+        marks.append(self._mark())
         if self.max_grad_norm is not None and self.max_grad_norm > 0:
             sumsq = torch.zeros((), dtype=torch.float32, device=f.grad.device)
             if self.strategy == "zero1":
@@ -161,11 +197,35 @@ class TrainEngine:
             norm, coef = K.clip_coef(sumsq, self.max_grad_norm)
             f.pending_grad_scale = coef
             self.last_grad_norm = norm
+        marks.append(self._mark())
         self.optimizer.step()
+        marks.append(self._mark())
         if self.strategy == "zero1":
             for b in self.plan.buckets:
-                self.plan.all_gather(f.master, b)
-            K.cast_f32_to_bf16(f.master, f.shadow)
+                self.plan.all_gather(f.shadow, b)
+            f.master_stale = True
+        marks.append(self._mark())
         if self.scheduler is not None:
             self.scheduler.step()
         self.model.zero_grad()
+        marks.append(self._mark())
+        if self.profile_phases:
+            torch.cuda.synchronize()
+            names = ["wait_comm", "grad_norm", "adam", "all_gather", "zero_grad"]
+            self.last_phase_ms = {n: marks[i].elapsed_time(marks[i + 1]) for i, n in enumerate(names)}
+
+    def _mark(self):
+        if not self.profile_phases:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def consolidate_master(self) -> None:
+        """ZeRO-1: bring the fp32 master of every slice up to date on every rank (collective; all ranks must call it).
+        The owner's fp32 values are authoritative; between optimizer steps only the bf16 compute copy is replicated."""
+        f = self.flat
+        if self.strategy == "zero1" and getattr(f, "master_stale", False):
+            for b in self.plan.buckets:
+                self.plan.all_gather(f.master, b)
+            f.master_stale = False

@@ -40,6 +40,10 @@ class FlatParams:
         self.shadow_version = -1
         self.params: list[nn.Parameter] = []
         self.pending_grad_scale: torch.Tensor | None = None  # clip coefficient folded into the next fused Adam step
+        # ZeRO-1 (engine.py): between optimizer steps only the owner's fp32 master slice and the replicated bf16 shadow
+        # are current; `master_consolidator` (a collective) refreshes the rest of the master on demand
+        self.master_stale = False
+        self.master_consolidator = None
 
     # ---- views
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -87,6 +91,10 @@ class FlatParams:
         self.shadow = self.shadow.to(device=self.master.device)
         self.shadow_version = -1
 
+    def consolidate(self) -> None:
+        if self.master_stale and self.master_consolidator is not None:
+            self.master_consolidator()
+
     # ---- shadow maintenance
     def current_version(self) -> int:
         # every in-place edit through torch (load_state_dict, torch optimizers, init) bumps the edited Parameter's
@@ -98,6 +106,9 @@ class FlatParams:
         optimizer, manual edits). The fused Adam keeps both in step without bumping any version counter."""
         v = self.current_version()
         if force or v != self.shadow_version:
+            # under ZeRO-1 a torch-side edit must rewrite the whole master on every rank (load_state_dict, broadcast);
+            # for partial edits call consolidate() first
+            self.master_stale = False
             if self.master.is_cuda:
                 from . import kernels as K
 

@@ -86,6 +86,12 @@ class _FlatModule(nn.Module):
         self.flat.zero_grad()
         self._ensure_grads_attached()
 
+    def state_dict(self, *args, **kwargs):
+        # ZeRO-1 replicates only the bf16 compute copy between steps; bring every rank's fp32 master up to date first
+        # (a collective: like DeepSpeed's consolidated state_dict, all ranks must call it)
+        self.flat.consolidate()
+        return super().state_dict(*args, **kwargs)
+
     def _ensure_grads_attached(self) -> None:
         for name, p in self.named_parameters():
             if p.grad is None:

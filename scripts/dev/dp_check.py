@@ -43,16 +43,25 @@ def main():
     ref_master = ref.flat.master.clone()
 
     ok = True
-    for strategy in ("ddp", "zero1"):
+    variants = [("ddp", {}), ("zero1", {}), ("zero1", {"overlap": False}), ("zero1", {"comm_max_ctas": 8}), ("ddp", {"comm_max_ctas": 8})]
+    for strategy, kw in variants:
         model = build(cfg, dev)
         opt = B200Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.95))
-        eng = TrainEngine(model, opt, None, max_grad_norm=1.0, gradient_accumulation_steps=ga, strategy=strategy)
+        eng = TrainEngine(model, opt, None, max_grad_norm=1.0, gradient_accumulation_steps=ga, strategy=strategy, **kw)
         for s in range(steps):
             for m in range(ga):
                 ids = data[s, m, rank].to(dev)
                 eng.manual_training_step({"input_ids": ids, "labels": ids})
             eng.manual_optimization_step()
         torch.cuda.synchronize()
+        if strategy == "zero1":
+            # between steps only the bf16 compute copy is replicated; the fp32 master of foreign slices is stale until
+            # state_dict() / consolidate_master()
+            shadow_before = model.flat.shadow.clone()
+            assert model.flat.master_stale
+            model.state_dict()
+            assert not model.flat.master_stale
+            assert torch.equal(shadow_before, model.flat.master.to(torch.bfloat16)), "replicated bf16 copy != bf16(owner's fp32 master)"
         upd_ref = ref_master - build(cfg, dev).flat.master
         upd = model.flat.master - build(cfg, dev).flat.master
         err = ((upd - upd_ref).norm() / upd_ref.norm()).item()
@@ -67,7 +76,7 @@ def main():
         good = err < 5e-2 and shadow_ok and same
         ok = ok and good
         if rank == 0:
-            print(f"{strategy}: update rel err vs single-process {err:.3e}, shadow in sync {shadow_ok}, ranks identical {same} -> {'OK' if good else 'FAIL'}", flush=True)
+            print(f"{strategy}{kw or ''}: update rel err vs single-process {err:.3e}, shadow in sync {shadow_ok}, ranks identical {same} -> {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -62,8 +62,16 @@ def _worker(rank, world, port, q):
         for lo, hi in owned:  # moments packed back to back, like B200Adam.set_shard
             _adam_ref(master[lo:hi], g[lo:hi] * coef, m[off:off + hi - lo], v[off:off + hi - lo], 1)
             off += hi - lo
+        # what the engine replicates between steps is the bf16 compute copy of the owned slices (2 B/param) ...
+        shadow = torch.zeros(N, dtype=torch.bfloat16)
+        for lo, hi in owned:
+            shadow[lo:hi] = master[lo:hi].to(torch.bfloat16)
+        for b in plan.buckets:
+            plan.all_gather(shadow, b)
+        # ... and the fp32 master only on demand (consolidate_master)
         for b in plan.buckets:
             plan.all_gather(master, b)
+        assert torch.equal(shadow, master.to(torch.bfloat16))
         # single-process reference with the averaged gradient
         ref = master0.clone()
         _adam_ref(ref, mean_grad * coef, torch.zeros(N), torch.zeros(N), 1)
