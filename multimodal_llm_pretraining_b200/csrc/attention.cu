@@ -125,10 +125,7 @@ struct FwdSmem {
 // When S (double-buffered) and O need <= 256 TMEM columns (head_dim 64 with 64-key blocks) and the tiles fit in < 113 KB, two
 // CTAs are resident per SM and cover each other's prologue / epilogue / barrier round trips.
 template <int D, int BN, int STAGES, bool DROP>
-#ifndef B200_DBG_FWD_DROP_MINB
-#define B200_DBG_FWD_DROP_MINB 2
-#endif
-__global__ void __launch_bounds__(192, (2 * BN + D <= 256) ? (DROP ? B200_DBG_FWD_DROP_MINB : 2) : 1)
+__global__ void __launch_bounds__(192, (2 * BN + D <= 256) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     using L = FwdSmem<D, BN, STAGES>;
@@ -1548,14 +1545,9 @@ static int launch_fwd_impl(const b200_attn_args* a, cudaStream_t st) {
     if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, BN))) return rc;
     if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, BN))) return rc;
     auto kern = attn_fwd_kernel<D, BN, STAGES, DROP>;
-    static const int dbg_pad = getenv("B200_DBG_FWD_SMEM_PAD") ? atoi(getenv("B200_DBG_FWD_SMEM_PAD")) : 0;  // TEMPORARY triage
-    static const int dbg_keep = getenv("B200_DBG_FWD_KEEPALL") != nullptr;                                   // TEMPORARY triage
-    const size_t smem_bytes = L::TOTAL + static_cast<size_t>(dbg_pad) * 1024;
-    if ((rc = set_smem(kern, smem_bytes, "attention_fwd"))) return rc;
+    if ((rc = set_smem(kern, L::TOTAL, "attention_fwd"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    AttnParams prm = make_params(a);
-    if (dbg_keep) prm.drop_thr = 0, prm.drop_scale = 1.0f;
-    kern<<<grid, 192, smem_bytes, st>>>(tq, tk, tv, prm);
+    kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, make_params(a));
     return check_launch("attention_fwd");
 }
 
@@ -1688,9 +1680,12 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
         case 64: {
             static const bool one_cta = getenv("B200_ATTN_FWD_1CTA") != nullptr;  // perf triage only
-            // 64-key blocks, two CTAs per SM. The dropout instantiation of that variant faulted intermittently inside a
-            // 24-layer model (not reproducible stand-alone, root cause not found): dropout runs use the one-CTA layout,
-            // which is covered by tests/test_roberta_gpu.py::test_full_depth_training_steps_with_dropout.
+            // 64-key blocks, two CTAs per SM. The dropout instantiation of that variant (168 registers, the cap two resident
+            // CTAs leave) raises an illegal-address fault about once per 10^4 CTAs — only with two CTAs resident (padding the
+            // dynamic smem to force one per SM: clean), independent of the mask values (keep-all still faults), and not when
+            // compiled to 96 registers (scripts/dev/stress_fwd64_drop.py; triage log in DESIGN.md §8). Its memory-instruction
+            // mix is identical to the dropout-free build, which has never faulted. Root cause open; dropout runs use the
+            // one-CTA layout (tests/test_roberta_gpu.py::test_full_depth_training_steps_with_dropout).
             static const bool drop_2cta = getenv("B200_ATTN_FWD_DROP_2CTA") != nullptr;  // triage of that fault only
             if (one_cta || (a->dropout_p > 0.f && !drop_2cta)) return launch_fwd<64, 128, 4>(a, st);
             return launch_fwd<64, 64, 3>(a, st);

@@ -221,6 +221,56 @@ class TrainEngine:
         e.record()
         return e
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, directory) -> None:
+        """HF-Trainer-style checkpoint directory: `pytorch_model.bin` (state_dict with HF key names, written by rank 0 after
+        the fp32 master is consolidated), `optimizer.pt` (replicated) or `optimizer_rank{r}.pt` (ZeRO-1: every rank saves the
+        moments of the slices it owns), `scheduler.pt`, `trainer_state.json`. Collective: all ranks call it."""
+        import json
+        from pathlib import Path
+
+        d = Path(directory)
+        rank = self.plan.rank if self.plan is not None else 0
+        if rank == 0:
+            d.mkdir(parents=True, exist_ok=True)
+        if self.plan is not None:
+            dist.barrier(group=self.plan.group)
+        sd = self.model.state_dict()  # consolidates the master under ZeRO-1 (collective)
+        if rank == 0:
+            torch.save({k: v.detach().cpu() for k, v in sd.items()}, d / "pytorch_model.bin")
+            if self.scheduler is not None:
+                torch.save(self.scheduler.state_dict(), d / "scheduler.pt")
+            (d / "trainer_state.json").write_text(json.dumps({
+                "global_step": self.micro // self.ga, "micro_step": self.micro, "strategy": self.strategy,
+                "world_size": self.plan.W if self.plan is not None else 1, "gradient_accumulation_steps": self.ga}))
+        if self.strategy == "zero1":
+            torch.save(self.optimizer.state_dict(), d / f"optimizer_rank{rank}.pt")
+        elif rank == 0:
+            torch.save(self.optimizer.state_dict(), d / "optimizer.pt")
+        if self.plan is not None:
+            dist.barrier(group=self.plan.group)
+
+    def load_checkpoint(self, directory) -> None:
+        """Inverse of save_checkpoint for the same strategy and world size (optimizer shards are per rank)."""
+        import json
+        from pathlib import Path
+
+        d = Path(directory)
+        state = json.loads((d / "trainer_state.json").read_text())
+        W = self.plan.W if self.plan is not None else 1
+        if state["strategy"] != self.strategy or state["world_size"] != W:
+            raise ValueError(f"checkpoint was written with strategy {state['strategy']!r} on {state['world_size']} rank(s); "
+                             f"this engine runs {self.strategy!r} on {W}")
+        rank = self.plan.rank if self.plan is not None else 0
+        self.model.load_state_dict(torch.load(d / "pytorch_model.bin", map_location="cpu"))
+        self.flat.sync_shadow(force=True)
+        opt_file = d / (f"optimizer_rank{rank}.pt" if self.strategy == "zero1" else "optimizer.pt")
+        self.optimizer.load_state_dict(torch.load(opt_file, map_location="cpu"))
+        if self.scheduler is not None and (d / "scheduler.pt").exists():
+            self.scheduler.load_state_dict(torch.load(d / "scheduler.pt", map_location="cpu"))
+        self.micro = int(state["micro_step"])
+        self.model.zero_grad()
+
     def consolidate_master(self) -> None:
         """ZeRO-1: bring the fp32 master of every slice up to date on every rank (collective; all ranks must call it).
         The owner's fp32 values are authoritative; between optimizer steps only the bf16 compute copy is replicated."""

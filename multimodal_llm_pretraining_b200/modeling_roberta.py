@@ -76,7 +76,7 @@ class _TiedDecoder(nn.Module):
 
 
 class B200RobertaForMaskedLM(_FlatModule):
-    supports_gradient_checkpointing = False
+    supports_gradient_checkpointing = True
     main_input_name = "input_ids"
 
     def __init__(self, config, allow_missing_attention_dropout: bool = False):
@@ -141,6 +141,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         head.decoder = _TiedDecoder(emb.word_embeddings.weight, head.bias)
         self.lm_head = head
         self.grad_ready_hook = None
+        self.gradient_checkpointing = False
         self._step_seed = 0  # bumped once per training forward: every micro-batch draws fresh masks
         self._cur_seed = 0   # the seed base of the forward/backward currently running
         self.reset_parameters()
@@ -182,7 +183,16 @@ class B200RobertaForMaskedLM(_FlatModule):
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None) -> None:
-        raise NotImplementedError("activation checkpointing is built for the GPT-NeoX path only")
+        """Per-layer activation checkpointing (src/train.py:112): keep only each layer's input and recompute the layer in
+        backward. The dropout masks are pure functions of (step seed, site, element), so the recomputation reproduces them."""
+        self.gradient_checkpointing = True
+
+    def gradient_checkpointing_disable(self) -> None:
+        self.gradient_checkpointing = False
+
+    @property
+    def is_gradient_checkpointing(self) -> bool:
+        return self.gradient_checkpointing
 
     @property
     def device(self) -> torch.device:
@@ -321,8 +331,12 @@ class B200RobertaForMaskedLM(_FlatModule):
         x, emb_saved = self._embed(ids, True)
         saved_layers = []
         for i in range(self.L):
-            x, sv = self._layer_fwd(i, x, B, S, True)
-            saved_layers.append(sv)
+            if self.gradient_checkpointing:
+                saved_layers.append(x)  # recompute the layer in backward
+                x, _ = self._layer_fwd(i, x, B, S, True)
+            else:
+                x, sv = self._layer_fwd(i, x, B, S, True)
+                saved_layers.append(sv)
         logits, head_saved = self._head_logits(x, keep=True)
         loss, _ = K.cross_entropy_(logits, labels.reshape(-1), V=self.V, write_grad=True)
         ctx = SimpleNamespace(ids=ids, B=B, S=S, emb=emb_saved, layers=saved_layers, head=head_saved, dlogits=logits, seed=self._cur_seed)
@@ -354,7 +368,10 @@ class B200RobertaForMaskedLM(_FlatModule):
         if hook:
             hook(*buckets[0])
         for i in reversed(range(self.L)):
-            dx = self._layer_bwd(i, ctx.layers[i], dx, B, S, True)
+            sv = ctx.layers[i]
+            if isinstance(sv, torch.Tensor):  # checkpointed: recompute this layer's activations (same masks: seed restored above)
+                _, sv = self._layer_fwd(i, sv, B, S, True)
+            dx = self._layer_bwd(i, sv, dx, B, S, True)
             ctx.layers[i] = None
             if hook:
                 hook(*buckets[1 + (self.L - 1 - i)])

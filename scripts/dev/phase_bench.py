@@ -69,13 +69,19 @@ def main():
         if s > 0:
             rows.append(d)
     t = torch.tensor(rows, dtype=torch.float64, device=dev).mean(0)
+    per_rank = None
     if world > 1:
+        mine = torch.stack([t[:-2].mean(), t[-2], t[-1]])
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 2) for v in a] for a in allr]  # [plain micro, boundary micro, optim] per rank
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t = t.tolist()
     if rank == 0:
         print(json.dumps({"world": world, "strategy": strategy, "overlap": not a.no_overlap, "model": a.model,
                           "micro_ms_plain_mean": sum(t[:-2]) / max(1, len(t) - 2), "micro_ms_each": t[:-1],
-                          "micro_ms_boundary": t[-2], "optim_ms": t[-1], "optim_phases_ms": getattr(eng, "last_phase_ms", None)}), flush=True)
+                          "micro_ms_boundary": t[-2], "optim_ms": t[-1], "optim_phases_ms": getattr(eng, "last_phase_ms", None),
+                          "per_rank_plain_boundary_optim_ms": per_rank}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

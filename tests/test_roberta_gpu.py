@@ -199,3 +199,21 @@ def test_full_depth_training_steps_with_dropout(dev, p_attn):
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses))), losses
     assert abs(losses[0] - 10.9) < 0.5 and losses[-1] < losses[0], losses  # ln(50265) = 10.82 at random init; it learns
+
+
+def test_activation_checkpointing_reproduces_gradients_with_dropout(gold, dev):
+    """Recomputing a layer in backward must regenerate the same dropout masks (they are functions of (step seed, site,
+    element)): gradients with and without per-layer checkpointing agree to the fp32-accumulation noise of the wgrad
+    reductions (split-K partial sums meet through red.add in arbitrary order)."""
+    ids = gold["batches"][0]
+    grads = []
+    for ckpt in (False, True):
+        m = build(gold, dev, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+        if ckpt:
+            m.gradient_checkpointing_enable()
+            assert m.is_gradient_checkpointing
+        loss = m(input_ids=ids.to(dev), labels=ids.to(dev))["loss"]
+        loss.backward()
+        grads.append((loss.item(), m.flat.grad.clone()))
+    assert grads[0][0] == grads[1][0]
+    assert rel(grads[1][1], grads[0][1]) <= 1e-5
