@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1"])
     ap.add_argument("--checkpointing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-tokens", type=int, default=256)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=1024,
+                    help="predicted tokens of the bounded CPU sample (one sequence): ~10 s per step on 16 cores, two steps")
     return ap.parse_args()
 
 

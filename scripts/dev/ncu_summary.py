@@ -39,7 +39,7 @@ print(f"# per-launch ncu --set full counters (cold-cache, serialised); HBM fract
 print(f"{'kernel':58s} {'time us':>9s} {'dram rd MB':>10s} {'dram wr MB':>10s} {'GB/s':>7s} {'of HBM':>6s} {'tensor%':>7s} {'sm%':>5s} {'L2hit%':>6s} {'regs':>4s} {'grid':>6s} {'blk':>4s} {'SM MHz':>6s}")
 for r in rows[2:]:
     name = r[col["Kernel Name"]]
-    if "b200::" not in name:
+    if "at::" in name or "cub::" in name:  # torch's own fill / random / copy kernels of the set-up code
         continue
     name = name.replace("void ", "").replace("b200::", "").split("(")[0]
     t, rd, wr = val(r, "t_us"), val(r, "rd"), val(r, "wr")

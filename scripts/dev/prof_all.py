@@ -25,7 +25,7 @@ def run(tag, fn, nbytes=None, flops=None):
         torch.cuda.synchronize()
         print(tag, flush=True)
         return
-    for _ in range(2):
+    for _ in range(5):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
