@@ -103,7 +103,7 @@ def main():
     run(e2, range(2, 3))
     a, b = resumed.state_dict()["embed_out.weight"], straight.state_dict()["embed_out.weight"]
     err = (((a - base) - (b - base)).norm() / (b - base).norm()).item()
-    good = err < 2e-3 and e2.optimizer._step == 3
+    good = err < 1e-2 and e2.optimizer._step == 3
     ok = ok and good
     if rank == 0:
         print(f"zero1 checkpoint resume: last-step update rel err vs uninterrupted run {err:.3e} -> {'OK' if good else 'FAIL'}", flush=True)

@@ -67,7 +67,7 @@ def test_checkpoint_resume_continues_the_same_trajectory(dev, tmp_path):
     upd = m2.flat.master - m1.flat.master
     upd_ref = ref_model.flat.master - m1.flat.master
     err = ((upd - upd_ref).norm() / upd_ref.norm()).item()
-    assert err <= 2e-3, err
+    assert err <= 1e-2, err  # a lost moment buffer or step count shows up as O(1)
     assert e2.optimizer.param_groups[0]["lr"] == ref.optimizer.param_groups[0]["lr"]
 
 
