@@ -33,6 +33,7 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             const int32_t* __restrict__ chunk_len, const int32_t* __restrict__ chunk_group,
             const int64_t* __restrict__ chunk_state, const AdamGroups groups, const float* __restrict__ grad_scale,
             int zero_grad) {
+    pdl_prologue();
     const int64_t start = chunk_start[blockIdx.x];
     const int len = chunk_len[blockIdx.x];
     const b200_adam_group h = groups.g[chunk_group[blockIdx.x]];
@@ -69,6 +70,7 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
 }
 
 __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ x, size_t n, float* out) {
+    pdl_prologue();
     __shared__ float sm[16];
     float s = 0.f;
     const size_t n4 = n / 4;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(512) sumsq_kernel(const float* __restrict__ x,
 }
 
 __global__ void clip_coef_kernel(const float* sumsq, float max_norm, float* norm_out, float* coef_out) {
+    pdl_prologue();
     const float nrm = sqrtf(*sumsq);
     if (norm_out) *norm_out = nrm;
     float c = 1.0f;
@@ -110,7 +113,7 @@ extern "C" int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf
     if (n_chunks == 0) return 0;
     AdamGroups gs;
     for (int i = 0; i < n_groups; ++i) gs.g[i] = groups[i];
-    adam_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), state_base,
+    launch_k(adam_kernel, dim3(n_chunks), dim3(256), 0, as_stream(stream), p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), state_base,
                                                          chunk_start, chunk_len, chunk_group, chunk_state, gs, grad_scale_dev, zero_grad);
     return check_launch("adam_step");
 }
@@ -121,10 +124,10 @@ extern "C" int b200_sumsq(const float* x, size_t n, float* out, b200_stream_t st
     const size_t cap = static_cast<size_t>(num_sms()) * 4;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    sumsq_kernel<<<static_cast<int>(blocks), 512, 0, as_stream(stream)>>>(x, n, out);
+    launch_k(sumsq_kernel, dim3(static_cast<int>(blocks)), dim3(512), 0, as_stream(stream), x, n, out);
     return check_launch("sumsq");
 }
 extern "C" int b200_clip_coef(const float* sumsq, float max_norm, float* norm_out, float* coef_out, b200_stream_t stream) {
-    clip_coef_kernel<<<1, 1, 0, as_stream(stream)>>>(sumsq, max_norm, norm_out, coef_out);
+    launch_k(clip_coef_kernel, dim3(1), dim3(1), 0, as_stream(stream), sumsq, max_norm, norm_out, coef_out);
     return check_launch("clip_coef");
 }

@@ -1,4 +1,6 @@
 // libb200pt: ABI version, thread-local error reporting, one-time init.
+#include <stdlib.h>
+
 #include "api.h"
 
 namespace b200 {
@@ -26,6 +28,14 @@ int num_sms() {
             g_num_sms = 148;  // B200
     }
     return g_num_sms;
+}
+
+bool pdl_enabled() {
+    // Off by default: on the power-capped B200s of this pool (1 kW, ~1.3 GHz under load) closing the inter-kernel gaps did
+    // not raise throughput (Pythia-1b step, same box, alternating runs: 178.4 / 178.6 k tokens/s without, 177.7 / 177.7 k with
+    // — the step is energy-limited, and idle gaps are what lets the clock boost between them). B200_PDL=1 enables it.
+    static const bool on = getenv("B200_PDL") && atoi(getenv("B200_PDL")) != 0;
+    return on;
 }
 
 int resolve_driver();  // gemm.cu

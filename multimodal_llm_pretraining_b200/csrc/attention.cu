@@ -185,6 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
 
     if (warp == 4) {
         // ---------------------------------------------------------------- TMA producer (one elected thread)
@@ -454,6 +455,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
     if (tr && threadIdx.x == 0) g_attn_trace[8001] = clock64();
 
     if (warp == 4) {
@@ -689,6 +691,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                   int B, int S, int H, int D, int64_t row_stride, int64_t head_stride) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t total = static_cast<int64_t>(B) * S * H;
     for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
@@ -820,6 +823,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
     if (tr) g_attn_trace[8101] = clock64();
 
     if (warp == 4) {
@@ -1204,6 +1208,7 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
     // Four 32 KB slots hold the K and V tiles. A V tile is dead once dP of its tile is done (early), a K tile only after
     // dQ (late); a TMA load takes ~2000 clocks. So tile t+2's K goes into the slot V_t just left (2 tiles of lead) and its
     // V into K_t's slot: each slot is used once every two tiles, alternating roles.
@@ -1547,7 +1552,7 @@ static int launch_fwd_impl(const b200_attn_args* a, cudaStream_t st) {
     auto kern = attn_fwd_kernel<D, BN, STAGES, DROP>;
     if ((rc = set_smem(kern, L::TOTAL, "attention_fwd"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, make_params(a));
+    launch_k(kern, dim3(grid), dim3(192), L::TOTAL, st, tq, tk, tv, make_params(a));
     return check_launch("attention_fwd");
 }
 
@@ -1568,7 +1573,7 @@ static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
     auto kern = attn_fwd256_kernel;
     if ((rc = set_smem(kern, L::TOTAL, "attention_fwd256"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(tq, tk, tv, to, make_params(a));
+    launch_k(kern, dim3(grid), dim3(192), L::TOTAL, st, tq, tk, tv, to, make_params(a));
     return check_launch("attention_fwd256");
 }
 
@@ -1599,7 +1604,7 @@ static int launch_bwd_impl(const b200_attn_args* a, cudaStream_t st, bool store_
         prm.p_out = static_cast<__nv_bfloat16*>(a->p_scratch);
         prm.ds_out = static_cast<__nv_bfloat16*>(a->ds_scratch);
     }
-    kern<<<grid, 192, L::TOTAL, st>>>(r1, r2, t1, t2, prm);
+    launch_k(kern, dim3(grid), dim3(192), L::TOTAL, st, r1, r2, t1, t2, prm);
     return check_launch(DKV ? "attention_bwd_dkv" : "attention_bwd_dq");
 }
 
@@ -1627,7 +1632,7 @@ static int launch_bwd_dq256(const b200_attn_args* a, cudaStream_t st) {
     auto kern = attn_bwd_dq256_kernel;
     if ((rc = set_smem(kern, L::TOTAL, "attention_bwd_dq256"))) return rc;
     dim3 grid((a->S + 127) / 128, a->H, a->B);
-    kern<<<grid, 192, L::TOTAL, st>>>(tdo, tk, tv, tp, tds, tdq, tq, make_params(a));
+    launch_k(kern, dim3(grid), dim3(192), L::TOTAL, st, tdo, tk, tv, tp, tds, tdq, tq, make_params(a));
     return check_launch("attention_bwd_dq256");
 }
 
@@ -1713,7 +1718,7 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
         int64_t blocks = (total_warps + 7) / 8;
         const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
         if (blocks > cap) blocks = cap;
-        attn_delta_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a->o), static_cast<const __nv_bfloat16*>(a->d_o),
+        launch_k(attn_delta_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(a->o), static_cast<const __nv_bfloat16*>(a->d_o),
                                                                     a->delta, a->B, a->S, a->H, a->D, a->o_row_stride, a->o_head_stride);
         if ((rc = check_launch("attention_delta"))) return rc;
     }

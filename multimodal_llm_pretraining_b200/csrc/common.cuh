@@ -112,6 +112,20 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): with B200_PDL=1 every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (api.h: launch_k). pdl_trigger() lets the NEXT kernel of the stream start its CTAs as soon as SMs free up (they run
+// their set-up: barrier init, TMEM allocation, descriptor prefetch); pdl_wait() blocks until EVERY CTA of the previous
+// kernel has exited and its memory operations are visible. Rule for all kernels here: no global-memory access (loads,
+// stores, TMA) before pdl_wait(). Both are no-ops for a kernel launched without the attribute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -61,6 +61,7 @@ __device__ __forceinline__ float block_reduce_sum_n(float v, float* sm) {
 __global__ void __launch_bounds__(CE_THREADS)
 ce_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
           const int* __restrict__ n_valid, int V, int64_t ld, int64_t ignore_index, int write_grad) {
+    pdl_prologue();
     __shared__ float sm[CE_THREADS / 32];
     __shared__ float s_xlabel;
     const int row = blockIdx.x;
@@ -160,6 +161,7 @@ constexpr int CE2_THREADS = 512;
 __global__ void __launch_bounds__(CE2_THREADS, 2)
 ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
                const int* __restrict__ n_valid, int T, int V, int64_t ld, int64_t ignore_index, int write_grad) {
+    pdl_prologue();
     extern __shared__ __align__(16) uint8_t ce_smem[];
     __shared__ float sm[CE2_THREADS / 32];
     __shared__ uint64_t bar;
@@ -284,6 +286,7 @@ ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ l
 }
 
 __global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* __restrict__ labels, int T, int64_t ignore_index, int* out) {
+    pdl_prologue();
     __shared__ int sm[32];
     int c = 0;
     for (int i = threadIdx.x; i < T; i += blockDim.x) c += (labels[i] != ignore_index);
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* __rest
 }
 // deterministic: fixed per-thread strided order, then fixed tree
 __global__ void __launch_bounds__(1024) mean_loss_kernel(const float* __restrict__ row_loss, const int* __restrict__ n_valid, int T, float* out) {
+    pdl_prologue();
     __shared__ float sm[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < T; i += blockDim.x) s += row_loss[i];
@@ -321,7 +325,7 @@ using namespace b200;
 
 extern "C" int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int* n_valid, b200_stream_t stream) {
     B200_REQUIRE(T > 0, "count_valid: T must be positive");
-    count_valid_kernel<<<1, 1024, 0, as_stream(stream)>>>(labels, T, ignore_index, n_valid);
+    launch_k(count_valid_kernel, dim3(1), dim3(1024), 0, as_stream(stream), labels, T, ignore_index, n_valid);
     return check_launch("count_valid");
 }
 extern "C" int b200_cross_entropy(void* logits, const int64_t* labels, float* row_loss, const int* n_valid, int T, int V,
@@ -340,15 +344,15 @@ extern "C" int b200_cross_entropy(void* logits, const int64_t* labels, float* ro
         const int per_sm = row_bytes <= 110 * 1024 ? 2 : 1;  // two rows per SM when they fit next to each other
         int grid = num_sms() * per_sm;
         if (grid > T) grid = T;
-        ce_smem_kernel<<<grid, CE2_THREADS, row_bytes, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, T, V, ld,
+        launch_k(ce_smem_kernel, dim3(grid), dim3(CE2_THREADS), row_bytes, as_stream(stream), static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, T, V, ld,
                                                                             ignore_index, write_grad);
         return check_launch("cross_entropy");
     }
     B200_REQUIRE(ld <= static_cast<int64_t>(CE_THREADS) * CE_NV * 8, "cross_entropy: ld %lld > %d unsupported", (long long)ld, CE_THREADS * CE_NV * 8);
-    ce_kernel<<<T, CE_THREADS, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, V, ld, ignore_index, write_grad);
+    launch_k(ce_kernel, dim3(T), dim3(CE_THREADS), 0, as_stream(stream), static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, V, ld, ignore_index, write_grad);
     return check_launch("cross_entropy");
 }
 extern "C" int b200_mean_loss(const float* row_loss, const int* n_valid, int T, float* loss_out, b200_stream_t stream) {
-    mean_loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, n_valid, T, loss_out);
+    launch_k(mean_loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_loss, n_valid, T, loss_out);
     return check_launch("mean_loss");
 }

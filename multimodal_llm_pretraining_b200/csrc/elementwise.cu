@@ -15,6 +15,7 @@ static inline int ew_grid(size_t n_vec, int threads) {
 
 // ----------------------------------------------------------------------------------------------- GELU
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t n_vec) {
+    pdl_prologue();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const uint4 v = ld_nc_v4(x + i);
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__
 }
 __global__ void __launch_bounds__(256)
 gelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, size_t n_vec) {
+    pdl_prologue();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const uint4 v = ld_nc_v4(x + i);
@@ -53,6 +55,7 @@ gelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4
 __global__ void __launch_bounds__(256)
 rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                 int T, int S, int nh, int hd, int half, int inverse) {
+    pdl_prologue();
     const int vec_per = half / 8;  // vectors per (token, head, q|k)
     const size_t total = static_cast<size_t>(T) * nh * 2 * vec_per;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -90,6 +93,7 @@ rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t
 __global__ void __launch_bounds__(256)
 rope_scalar_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                    int T, int S, int nh, int hd, int half, int inverse) {
+    pdl_prologue();
     const size_t total = static_cast<size_t>(T) * nh * 2 * half;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -117,6 +121,7 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __re
                      const int64_t* __restrict__ ids1, const __nv_bfloat16* __restrict__ t1,
                      const int64_t* __restrict__ ids2, const __nv_bfloat16* __restrict__ t2,
                      __nv_bfloat16* __restrict__ out, int T, int h) {
+    pdl_prologue();
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
@@ -162,6 +167,7 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dout, float* __restrict__ dtable,
                      int T, int h, int64_t skip_id) {
+    pdl_prologue();
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
@@ -185,6 +191,7 @@ embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __res
 // ----------------------------------------------------------------------------------------------- casts
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n_vec4) {
+    pdl_prologue();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec4;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const float4 v = src[i];
@@ -192,11 +199,13 @@ cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, si
     }
 }
 __global__ void cast_f32_bf16_tail(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t start, size_t n) {
+    pdl_prologue();
     const size_t i = start + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 __global__ void __launch_bounds__(256)
 scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scale_dev, float scale_host) {
+    pdl_prologue();
     const float s = (scale_dev ? *scale_dev : 1.0f) * scale_host;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -209,6 +218,7 @@ scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scal
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int64_t ld, int rows_per_chunk,
                       float* __restrict__ partial) {
+    pdl_prologue();
     __shared__ float sm[8][32][9];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int col = (blockIdx.x * 32 + cx) * 8;
@@ -245,6 +255,7 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, i
 }
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ out) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     float t = 0.f;
@@ -258,6 +269,7 @@ colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int col
 // One warp per row: inclusive warp scan over 32-token chunks with a running carry. Integer-exact.
 __global__ void __launch_bounds__(128)
 position_ids_kernel(const int64_t* __restrict__ ids, int64_t* __restrict__ pos, int B, int S, int64_t pad) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B) return;
@@ -294,6 +306,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
 __global__ void __launch_bounds__(256)
 dropout_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual, uint4* __restrict__ out, size_t n_vec,
                uint32_t thr16, float keep_scale, uint64_t seed) {
+    pdl_prologue();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_vec;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const uint4 v = ld_nc_v4(x + i);
@@ -323,13 +336,13 @@ using namespace b200;
 extern "C" int b200_gelu_fwd(const void* x, void* y, size_t n, b200_stream_t stream) {
     B200_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(y), "gelu_fwd: n must be a multiple of 8 and pointers 16B aligned");
     const size_t nv = n / 8;
-    gelu_fwd_kernel<<<ew_grid(nv, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), nv);
+    launch_k(gelu_fwd_kernel, dim3(ew_grid(nv, 256)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(x), static_cast<uint4*>(y), nv);
     return check_launch("gelu_fwd");
 }
 extern "C" int b200_gelu_bwd(const void* x, const void* dy, void* dx, size_t n, b200_stream_t stream) {
     B200_REQUIRE(n % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx), "gelu_bwd: n must be a multiple of 8 and pointers 16B aligned");
     const size_t nv = n / 8;
-    gelu_bwd_kernel<<<ew_grid(nv, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(dy), static_cast<uint4*>(dx), nv);
+    launch_k(gelu_bwd_kernel, dim3(ew_grid(nv, 256)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(x), static_cast<const uint4*>(dy), static_cast<uint4*>(dx), nv);
     return check_launch("gelu_bwd");
 }
 
@@ -341,10 +354,10 @@ extern "C" int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float
     auto p = static_cast<__nv_bfloat16*>(qkv);
     if (half % 8 == 0 && hd % 8 == 0 && aligned16(qkv)) {
         const size_t total = static_cast<size_t>(T) * nh * 2 * (half / 8);
-        rope_vec_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
+        launch_k(rope_vec_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, as_stream(stream), p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
     } else {
         const size_t total = static_cast<size_t>(T) * nh * 2 * half;
-        rope_scalar_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
+        launch_k(rope_scalar_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, as_stream(stream), p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
     }
     return check_launch("rope_qk_inplace");
 }
@@ -354,7 +367,7 @@ extern "C" int b200_embedding3_fwd(const int64_t* ids0, const void* table0, cons
                                    b200_stream_t stream) {
     B200_REQUIRE(h % 8 == 0 && aligned16(table0) && aligned16(out), "embedding_fwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    embedding_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+    launch_k(embedding_fwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), 
         ids0, static_cast<const __nv_bfloat16*>(table0), ids1, static_cast<const __nv_bfloat16*>(table1), ids2,
         static_cast<const __nv_bfloat16*>(table2), static_cast<__nv_bfloat16*>(out), T, h);
     return check_launch("embedding_fwd");
@@ -369,26 +382,26 @@ extern "C" int b200_embedding_bwd(const int64_t* ids, const void* dout, float* d
     (void)vocab;
     B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, -1);
+    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, -1);
     return check_launch("embedding_bwd");
 }
 extern "C" int b200_embedding_bwd_padding(const int64_t* ids, const void* dout, float* dtable, int T, int h, int64_t padding_idx,
                                           b200_stream_t stream) {
     B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    embedding_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, padding_idx);
+    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, padding_idx);
     return check_launch("embedding_bwd_padding");
 }
 
 extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200_stream_t stream) {
     B200_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0, "cast: src must be 16B and dst 8B aligned");
     const size_t n4 = n / 4;
-    if (n4) cast_f32_bf16_kernel<<<ew_grid(n4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n4);
-    if (n % 4) cast_f32_bf16_tail<<<1, 32, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), n4 * 4, n);
+    if (n4) launch_k(cast_f32_bf16_kernel, dim3(ew_grid(n4, 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n4);
+    if (n % 4) launch_k(cast_f32_bf16_tail, dim3(1), dim3(32), 0, as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), n4 * 4, n);
     return check_launch("cast_f32_to_bf16");
 }
 extern "C" int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream) {
-    scale_f32_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, scale_dev, scale_host);
+    launch_k(scale_f32_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, as_stream(stream), x, n, scale_dev, scale_host);
     return check_launch("scale_f32");
 }
 
@@ -405,16 +418,16 @@ extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, f
     const int rows_per_chunk = (rows + chunks - 1) / chunks;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
     float* part = static_cast<float*>(workspace);
-    colsum_partial_kernel<<<dim3(col_blocks, chunks), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, ld, rows_per_chunk, part);
+    launch_k(colsum_partial_kernel, dim3(col_blocks, chunks), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(x), rows, cols, ld, rows_per_chunk, part);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
-    colsum_finalize_kernel<<<(cols + 255) / 256, 256, 0, as_stream(stream)>>>(part, chunks, cols, out);
+    launch_k(colsum_finalize_kernel, dim3((cols + 255) / 256), dim3(256), 0, as_stream(stream), part, chunks, cols, out);
     return check_launch("colsum_finalize");
 }
 
 extern "C" int b200_roberta_position_ids(const int64_t* ids, int64_t* pos, int B, int S, int64_t pad_id, b200_stream_t stream) {
     B200_REQUIRE(B > 0 && S > 0, "position_ids: bad shape");
-    position_ids_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(ids, pos, B, S, pad_id);
+    launch_k(position_ids_kernel, dim3((B + 3) / 4), dim3(128), 0, as_stream(stream), ids, pos, B, S, pad_id);
     return check_launch("roberta_position_ids");
 }
 
@@ -424,7 +437,7 @@ extern "C" int b200_dropout(const void* x, const void* residual, void* out, size
     const uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float keep = 65536.0f / static_cast<float>(65536u - thr);
     const size_t n_vec = n / 8;
-    dropout_kernel<<<ew_grid(n_vec, 256), 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(residual),
+    launch_k(dropout_kernel, dim3(ew_grid(n_vec, 256)), dim3(256), 0, as_stream(stream), static_cast<const uint4*>(x), static_cast<const uint4*>(residual),
                                                                         static_cast<uint4*>(out), n_vec, thr, keep, seed);
     return check_launch("dropout");
 }

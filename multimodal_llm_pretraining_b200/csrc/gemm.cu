@@ -257,6 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
 
     // tile -> (z, tm, tn), first k block; identical in every role
     auto decode = [&](int unit, int& z, int& tm, int& tn, int& kb0, int& kb1) {
@@ -574,13 +575,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.cuh: pdl_trigger / pdl_wait
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmAux, p);
     if (e != cudaSuccess) return fail(-2, "gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     return check_launch("gemm_bf16");

@@ -31,6 +31,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1,
               __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
               __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
               int cols, float eps, int G) {
+    pdl_prologue();
     __shared__ float red[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows_per_block = 4 / G;
@@ -135,6 +136,7 @@ ln_fwd_persist_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
                       __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
                       __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
                       int cols, float eps, int G) {
+    pdl_prologue();
     __shared__ float red[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int groups = 8 / G;
@@ -229,6 +231,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
               const float* __restrict__ g1, const __nv_bfloat16* __restrict__ dy1, const float* __restrict__ g2,
               const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ dres,
               __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int rows, int cols, int G) {
+    pdl_prologue();
     __shared__ float red[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows_per_block = 8 / G;
@@ -366,6 +369,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mea
 __global__ void __launch_bounds__(256)
 ln_bwd_finalize(const float* __restrict__ partial, int n_partial, int n_arrays, int cols, float* o0, float* o1,
                 float* o2, float* o3) {
+    pdl_prologue();
     __shared__ float sm[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int arr = blockIdx.y;
@@ -417,8 +421,8 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
     if (grid > max_blocks) grid = max_blocks;
 #define LAUNCH(NVV)                                                                                                                   \
     do {                                                                                                                              \
-        if (gamma2) ln_fwd_persist_kernel<NVV, 2><<<grid, 256, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G); \
-        else ln_fwd_persist_kernel<NVV, 1><<<grid, 256, 0, st>>>(xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G);        \
+        if (gamma2) launch_k(ln_fwd_persist_kernel<NVV, 2>, dim3(grid), dim3(256), 0, st, xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G); \
+        else launch_k(ln_fwd_persist_kernel<NVV, 1>, dim3(grid), dim3(256), 0, st, xs, gamma, beta, y1s, gamma2, beta2, y2s, mean, rstd, rows, cols, eps, G);        \
     } while (0)
     switch (nv) {
         case 1: LAUNCH(1); break;
@@ -458,7 +462,7 @@ extern "C" int b200_layernorm_bwd(const void* x, const float* mean, const float*
     auto dxs = static_cast<__nv_bfloat16*>(dx);
     float* part = static_cast<float*>(workspace);
     cudaStream_t st = as_stream(stream);
-#define LAUNCH(NVV, NAA) ln_bwd_kernel<NVV, NAA><<<grid, 256, 0, st>>>(xs, mean, rstd, gamma, d1, gamma2, d2, dr, dxs, part, rows, cols, G)
+#define LAUNCH(NVV, NAA) launch_k(ln_bwd_kernel<NVV, NAA>, dim3(grid), dim3(256), 0, st, xs, mean, rstd, gamma, d1, gamma2, d2, dr, dxs, part, rows, cols, G)
     if (NA == 1) {
         switch (nv) {
             case 1: LAUNCH(1, 1); break;
@@ -483,6 +487,6 @@ extern "C" int b200_layernorm_bwd(const void* x, const float* mean, const float*
     int rc = check_launch("layernorm_bwd");
     if (rc) return rc;
     dim3 fgrid((cols + 31) / 32, NA * 2);
-    ln_bwd_finalize<<<fgrid, 256, 0, st>>>(part, grid * rows_per_block, NA * 2, cols, dgamma, dbeta, dgamma2, dbeta2);
+    launch_k(ln_bwd_finalize, dim3(fgrid), dim3(256), 0, st, part, grid * rows_per_block, NA * 2, cols, dgamma, dbeta, dgamma2, dbeta2);
     return check_launch("layernorm_bwd_finalize");
 }
