@@ -12,8 +12,10 @@ every rank runs independent micro-batches; the only exchange is per optimizer st
   strategy "zero1" : the same buckets are reduce-scattered (AVG) in place — rank r keeps slice r of every bucket —
                      local sum-of-squares + one scalar all-reduce give the global grad norm, the fused Adam updates
                      only the owned slices (moments exist only for them: 8 B/param/W) and writes their bf16 compute
-                     copy in the same pass; the bf16 slices (2 B/param — what the next forward reads) are all-gathered in
-                     place. The fp32 master of the slices a rank does not own goes stale, exactly as under DeepSpeed
+                     copy in the same pass; the bf16 slices (2 B/param — what the GEMMs of the next forward read) are
+                     all-gathered in place, and the 1-D parameters (biases, LayerNorm affine: read in fp32 by the kernels)
+                     are exchanged in fp32 through one small packed all-reduce. The fp32 master of the 2-D parameters a
+                     rank does not own goes stale, exactly as under DeepSpeed
                      ZeRO-1 where the fp32 master exists only on the owner; `consolidate_master()` (called by
                      `state_dict()`) all-gathers it on demand.
 
@@ -29,6 +31,7 @@ from __future__ import annotations
 
 from typing import Callable
 
+import math
 import os
 
 import torch
@@ -98,6 +101,23 @@ class CommPlan:
     def all_reduce_sum_scalar(self, x: torch.Tensor) -> None:
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
 
+    def owned_mask(self, idx: torch.Tensor) -> torch.Tensor:
+        """bool mask over the flat-buffer element indices `idx`: True where this rank owns the element."""
+        own = torch.zeros(int(idx.max().item()) + 1 if idx.numel() else 0, dtype=torch.bool)
+        for lo, hi in self.owned_ranges():
+            own[lo:hi] = True
+        return own[idx.cpu()].to(idx.device)
+
+    def exchange_owned(self, flat: torch.Tensor, idx: torch.Tensor, own: torch.Tensor) -> None:
+        """flat[idx] <- the owning rank's value, on every rank: owners contribute their elements to one packed buffer, the
+        others zeros, and a SUM all-reduce fills it in (x + 0 is exact)."""
+        if idx.numel() == 0:
+            return
+        vals = flat.index_select(0, idx)
+        packed = torch.where(own, vals, torch.zeros_like(vals))
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+        flat.index_copy_(0, idx, packed)
+
 
 class TrainEngine:
     """manual_training_step / manual_optimization_step of the reference harness (src/benchmarking/utils.py:61-80) for a
@@ -140,9 +160,29 @@ class TrainEngine:
             if strategy == "zero1":
                 optimizer.set_shard(self.plan.owned_ranges())
                 self.flat.master_consolidator = self.consolidate_master
+                self._build_fp32_exchange()
             # identical initial parameters everywhere (rank 0 wins), like DDP's constructor broadcast
             dist.broadcast(self.flat.master, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             self.flat.sync_shadow(force=True)
+
+    def _build_fp32_exchange(self) -> None:
+        """ZeRO-1 replicates the bf16 compute copy, but the kernels read biases and LayerNorm affine parameters (every 1-D
+        parameter) from the fp32 master. Those few elements (13 h per layer) are exchanged in fp32 after each optimizer step:
+        every rank contributes the elements it owns to one packed buffer, zeros elsewhere, and a SUM all-reduce fills it in."""
+        f = self.flat
+        dev = f.master.device
+        idx = []
+        for name in f.names:
+            if len(f.shapes[name]) < 2:
+                o = f.offsets[name]
+                idx.append(torch.arange(o, o + math.prod(f.alloc_shapes[name]), dtype=torch.int64))
+        self._fp32_idx = torch.cat(idx).to(dev) if idx else torch.empty(0, dtype=torch.int64, device=dev)
+        self._fp32_own = self.plan.owned_mask(self._fp32_idx)
+
+    def _exchange_fp32_params(self) -> None:
+        f = self.flat
+        self.plan.exchange_owned(f.master, self._fp32_idx, self._fp32_own)
+        f.shadow_version = f.current_version()  # a torch-side write to the master that must NOT trigger a shadow re-cast
 
     # ------------------------------------------------------------------ fwd + bwd of one micro-batch
     def _reduce_bucket(self, plan: CommPlan, b: tuple[int, int]) -> None:
@@ -203,7 +243,8 @@ class TrainEngine:
         if self.strategy == "zero1":
             for b in self.plan.buckets:
                 self.plan.all_gather(f.shadow, b)
-            f.master_stale = True
+            self._exchange_fp32_params()
+            f.master_stale = True  # of the 2-D parameters a rank does not own; nothing on the step path reads those
         marks.append(self._mark())
         if self.scheduler is not None:
             self.scheduler.step()
@@ -279,3 +320,4 @@ class TrainEngine:
             for b in self.plan.buckets:
                 self.plan.all_gather(f.master, b)
             f.master_stale = False
+            f.shadow_version = f.current_version()  # the bf16 copy is already bf16(master) everywhere

@@ -72,6 +72,20 @@ def _worker(rank, world, port, q):
         for b in plan.buckets:
             plan.all_gather(master, b)
         assert torch.equal(shadow, master.to(torch.bfloat16))
+        # the fp32 elements the kernels read directly (1-D parameters) travel through one packed SUM all-reduce
+        stale = torch.full((N,), float(rank + 7))          # every rank starts with its own (wrong) values ...
+        truth = torch.arange(N, dtype=torch.float32) * 0.5
+        for lo, hi in owned:
+            stale[lo:hi] = truth[lo:hi]                      # ... except the elements it owns
+        idx = torch.cat([torch.arange(100, 164), torch.arange(300, 700), torch.arange(1100, 1152)])
+        own_mask = plan.owned_mask(idx)
+        assert int(own_mask.sum()) == sum(max(0, min(hi, b) - max(lo, a)) for lo, hi in owned for a, b in [(100, 164), (300, 700), (1100, 1152)])
+        before = stale.clone()
+        plan.exchange_owned(stale, idx, own_mask)
+        assert torch.equal(stale[idx], truth[idx])
+        rest = torch.ones(N, dtype=torch.bool)
+        rest[idx] = False
+        assert torch.equal(stale[rest], before[rest])        # nothing else is touched
         # single-process reference with the averaged gradient
         ref = master0.clone()
         _adam_ref(ref, mean_grad * coef, torch.zeros(N), torch.zeros(N), 1)
