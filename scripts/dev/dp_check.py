@@ -99,6 +99,38 @@ def main():
             worst.append((((a_ - b_).norm() / (b_.norm() + 1e-30)).item(), n))
         for e_, n in sorted(worst, reverse=True)[:6]:
             print(f"    {n}: {e_:.3e}", flush=True)
+    # ---- RoBERTa (tied decoder, padded vocabulary, both dropouts on): the same bit-for-bit requirement
+    from multimodal_llm_pretraining_b200.modeling_roberta import B200RobertaForMaskedLM
+    from multimodal_llm_pretraining_b200.models.configs import roberta_large_config_dict
+
+    rcfg = dict(roberta_large_config_dict(), vocab_size=1001, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024)
+    rdata = torch.randint(3, 1001, (steps, ga, world, 4, 128), generator=torch.Generator().manual_seed(6))
+
+    def rbuild():
+        m_ = B200RobertaForMaskedLM(as_namespace(rcfg))
+        m_.reset_parameters(torch.Generator().manual_seed(3))
+        return m_.to(dev).train()
+
+    rfinal = {}
+    for strategy in ("ddp", "zero1"):
+        m_ = rbuild()
+        e_ = TrainEngine(m_, B200Adam(m_.parameters(), lr=1e-3, betas=(0.9, 0.98)), None, max_grad_norm=0.0, gradient_accumulation_steps=ga, strategy=strategy)
+        for s_ in range(steps):
+            for mb in range(ga):
+                ids = rdata[s_, mb, rank].to(dev)
+                e_.manual_training_step({"input_ids": ids, "labels": ids})
+            e_.manual_optimization_step()
+        rfinal[strategy] = {k: v.clone() for k, v in m_.state_dict().items()}
+    rinit = rbuild().state_dict()
+    num = sum(((rfinal["zero1"][k] - rfinal["ddp"][k]).double() ** 2).sum() for k in rinit) ** 0.5
+    den = sum(((rfinal["ddp"][k] - rinit[k]).double() ** 2).sum() for k in rinit) ** 0.5
+    rz = float(num / den)
+    moved = float(den) > 0
+    r_ok = moved and rz <= (0.0 if world == 2 else 1e-5)
+    ok = ok and r_ok
+    if rank == 0:
+        print(f"roberta zero1 vs ddp: update rel diff {rz:.3e} (update norm {float(den):.3e}) -> {'OK' if r_ok else 'FAIL'}", flush=True)
+
     # ---- ZeRO-1 checkpoint round trip: 2 steps, save (sharded optimizer state), fresh engine, load, 1 more step == 3 steps straight
     import tempfile
 

@@ -16,4 +16,4 @@ def test_ddp_and_zero1_match_single_process():
            "--master-port", "29611", str(ROOT / "scripts" / "dev" / "dp_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "ddp:" in res.stdout and "zero1:" in res.stdout and "FAIL" not in res.stdout
+    assert "ddp:" in res.stdout and "zero1:" in res.stdout and "roberta zero1 vs ddp" in res.stdout and "FAIL" not in res.stdout
