@@ -126,7 +126,9 @@ def main():
     den = sum(((rfinal["ddp"][k] - rinit[k]).double() ** 2).sum() for k in rinit) ** 0.5
     rz = float(num / den)
     moved = float(den) > 0
-    r_ok = moved and rz <= (0.0 if world == 2 else 1e-5)
+    # not bit-exact here: the embedding backward adds colliding token rows with fp32 atomics in arbitrary order (measured 3e-9);
+    # a stale parameter shows up at >= 1e-3
+    r_ok = moved and rz <= 1e-6
     ok = ok and r_ok
     if rank == 0:
         print(f"roberta zero1 vs ddp: update rel diff {rz:.3e} (update norm {float(den):.3e}) -> {'OK' if r_ok else 'FAIL'}", flush=True)
