@@ -1,3 +1,5 @@
+"""Triage: is a checkpoint resume bit-exact on one GPU? Compares restored master / shadow / moments with the live ones and the
+step taken from the restored state with the uninterrupted run."""
 import sys, tempfile
 sys.path.insert(0, "/root/repo")
 import torch
