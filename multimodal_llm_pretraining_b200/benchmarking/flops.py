@@ -27,3 +27,19 @@ def count_flops_per_example_measured(model_class: BaseModelClass, device: str = 
     with FlopCounterMode(display=False) as fc:
         model(input_ids=ids, labels=ids).get("loss").backward()
     return float(fc.get_total_flops())
+
+
+def estimate_training_days_from_flops(num_nodes: int, gpus_per_node: int, gpu_type: str, model_class: BaseModelClass,
+                                      training_flops: float | None = None) -> float:
+    """experiments/training_time_analytic.py:14-53 with the b200 row added (gpus.PEAK_TFLOPS): training days if every GPU ran
+    at its datasheet dense tensor peak (bf16 when the model trains in mixed precision, tf32 otherwise).
+    `training_flops` defaults to flops-per-example x batch size x training steps (experiments/count_flops.py)."""
+    from ..gpus import PEAK_TFLOPS
+
+    if gpu_type not in PEAK_TFLOPS:
+        raise NotImplementedError(gpu_type)
+    peak = PEAK_TFLOPS[gpu_type]["bf16" if model_class.mixed_precision is not None else "tf32"]
+    if training_flops is None:
+        training_flops = count_flops_per_example(model_class) * model_class.batch_size * model_class.training_steps
+    flops_per_day = num_nodes * gpus_per_node * peak * 1e12 * 86400.0
+    return training_flops / flops_per_day

@@ -123,3 +123,20 @@ def test_dummy_dataset_and_sharding_bit_exact():
     perm = torch.randperm(64, generator=torch.Generator().manual_seed(0))
     assert torch.equal(b0["input_ids"], ds.input_ids[perm[0:4]]) and torch.equal(b1["input_ids"], ds.input_ids[perm[4:8]])
     assert torch.equal(b0["labels"], b0["input_ids"])
+
+
+def test_analytic_training_days_with_b200_row():
+    """experiments/training_time_analytic.py:14-53: days = training FLOPs / (GPUs x datasheet peak x 86400), b200 row added."""
+    from multimodal_llm_pretraining_b200.benchmarking.flops import count_flops_per_example, estimate_training_days_from_flops
+    from multimodal_llm_pretraining_b200.gpus import PEAK_TFLOPS, ampere_or_newer_gpu
+    from multimodal_llm_pretraining_b200.models import get_model_class
+
+    mc = get_model_class("pythia-1b")
+    total = count_flops_per_example(mc) * mc.batch_size * mc.training_steps
+    assert count_flops_per_example(mc) == 12_817_874_812_992  # SURVEY §8d
+    days = estimate_training_days_from_flops(1, 8, "b200", mc)
+    assert days == pytest.approx(total / (8 * 2250e12 * 86400))
+    assert estimate_training_days_from_flops(1, 8, "h100", mc) == pytest.approx(days * 2250 / 756)
+    assert PEAK_TFLOPS["a100"] == {"bf16": 312.0, "tf32": 156.0} and ampere_or_newer_gpu("b200") and not ampere_or_newer_gpu("v100")
+    with pytest.raises(NotImplementedError):
+        estimate_training_days_from_flops(1, 8, "v100", mc)
