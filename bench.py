@@ -304,6 +304,16 @@ def main_b200(a):
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     per_gpu = value / world
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    # DRAM traffic of the GEMM variants from the committed `ncu --set full` capture (per launch, MB read + written)
+    ncu_traffic = {}
+    try:
+        names = ["fwd+bias qkv", "fwd+bias+gelu+aux mlp_up", "fwd+bias+residual mlp_down", "dgrad*dgelu", "dgrad+residual", "wgrad split-K"]
+        rows = [ln.split() for ln in (ROOT / "profiles" / "r01_ncu_all_kernels.txt").read_text().splitlines() if ln.startswith("gemm_kernel<")]
+        for nm, r in zip(names, rows):  # columns after the kernel name: time us, dram rd MB, dram wr MB, ...
+            k = next(i for i, tok in enumerate(r) if tok.endswith(">")) + 1
+            ncu_traffic[nm] = {"time_us": float(r[k]), "dram_mb": float(r[k + 1]) + float(r[k + 2])}
+    except Exception:
+        ncu_traffic = None
 
     if rank == 0:
         cpu = None
@@ -334,6 +344,8 @@ def main_b200(a):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
                 "frac": (achieved / peak_sust) if achieved else None, "traffic": None,
+                "ncu_dram_per_launch": ncu_traffic,  # per GEMM variant at the step's shapes (profiles/r01_ncu_all_kernels.txt); the
+                # aggregate above spans all variants, so there is no single per-launch `traffic` figure for it
                 "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all fwd/dgrad/wgrad launches of one step)",
                 "how": f"sum of 2*M*N*K over {len(prof)} launches / sum of their CUDA-event durations in a separate instrumented step; "
                        f"GEMM share of step {gemm_ms / step_ms_plain:.3f}; peak = {peak_src}",
