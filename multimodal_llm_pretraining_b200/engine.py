@@ -147,7 +147,8 @@ class TrainEngine:
                 raise RuntimeError("strategy %r needs an initialised torch.distributed process group" % strategy)
             W, r = dist.get_world_size(group), dist.get_rank(group)
             self.plan = CommPlan(model.comm_buckets(), W, r, group)
-            self.comm_stream = torch.cuda.Stream()
+            # host-side tests drive the exchange logic with CPU tensors over gloo: no side stream there
+            self.comm_stream = torch.cuda.Stream() if self.flat.master.is_cuda else None
             if comm_max_ctas is None:
                 comm_max_ctas = int(os.environ.get("B200_COMM_MAX_CTAS", "0")) or None
             if comm_max_ctas and overlap and dist.get_backend(group) == "nccl":
@@ -193,7 +194,7 @@ class TrainEngine:
 
     def _on_grads_ready(self, start: int, end: int) -> None:
         b = self.plan.bucket_of(start, end)
-        if not self.overlap:
+        if not self.overlap or self.comm_stream is None:
             self._pending.append(b)
             return
         ev = torch.cuda.Event()
@@ -221,7 +222,8 @@ class TrainEngine:
         f = self.flat
         marks = [self._mark()]
         if self.plan is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
             for b in self._pending:  # overlap=False: the bucket collectives run here, on the compute stream
                 self._reduce_bucket(self.plan, b)
             self._pending.clear()
