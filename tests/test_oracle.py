@@ -70,6 +70,29 @@ def test_oracle_matches_live_hf_when_available(gold):
     assert abs(ref.item() - got.item()) < 2e-5
 
 
+@pytest.mark.parametrize("hidden,heads", [(128, 2), (160, 2), (256, 2), (256, 1)], ids=["hd64", "hd80", "hd128", "hd256"])
+def test_oracle_matches_live_hf_at_every_head_shape(gold, hidden, heads):
+    """The GPU parity tests at head_dim 64 / 80 / 128 / 256 (the shapes of Pythia-160m..410m, 2.8b, 1.4b, 1b; rotary 16 / 20 /
+    32 / 64 dims) check the kernels against this oracle: pin it to the real HF module at each of those head shapes — loss
+    and every parameter gradient."""
+    tr = pytest.importorskip("transformers")
+    cfg = dict(gold["cfg"], hidden_size=hidden, num_attention_heads=heads, intermediate_size=4 * hidden, vocab_size=96)
+    torch.manual_seed(hidden + heads)
+    m = tr.GPTNeoXForCausalLM(tr.GPTNeoXConfig(**cfg, attn_implementation="eager")).float()
+    with torch.no_grad():  # non-trivial biases / LayerNorm parameters (HF initialises them to 0 / 1)
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    ids = torch.randint(0, 96, (2, 33))
+    ref = m(input_ids=ids, labels=ids).loss
+    ref.backward()
+    P = {k: v.detach().clone() for k, v in m.state_dict().items() if "inv_freq" not in k and "masked_bias" not in k and not k.endswith("attention.bias")}
+    loss, grads = O.neox_loss_and_grads(P, ids, ids, cfg)
+    assert abs(loss.item() - ref.item()) < 2e-5
+    for n, p in m.named_parameters():
+        assert torch.allclose(grads[n], p.grad, atol=2e-6, rtol=2e-4), n
+
+
 def test_schedule_matches_hf_formula():
     # Pythia: warmup 1430 of 143000 steps, min_lr_rate 0.1 (src/models/pythia.py:69-78)
     assert O.cosine_with_min_lr(0, 1430, 143000, 0.1) == 0.0
