@@ -122,6 +122,31 @@ def test_roberta_oracle_matches_hf_golden(rgold):
         assert torch.allclose(grads[k], g, atol=1e-6, rtol=1e-4), k
 
 
+def test_roberta_oracle_matches_live_hf_at_roberta_large_head_shape(rgold):
+    """head_dim 64 (roberta-large: 16 heads x 64), non-trivial biases, pad tokens inside the batch."""
+    tr = pytest.importorskip("transformers")
+    from oracle import roberta_oracle as R
+
+    cfg = dict(rgold["cfg"], hidden_size=128, num_attention_heads=2, intermediate_size=512)
+    torch.manual_seed(7)
+    m = tr.RobertaForMaskedLM(tr.RobertaConfig(**cfg, attn_implementation="eager")).float().eval()  # eval: dropout off
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.05)
+    ids = torch.randint(3, cfg["vocab_size"], (2, 40))
+    ids[0, 5] = ids[1, 0] = ids[1, 39] = cfg["pad_token_id"]  # positions skip pad tokens (create_position_ids_from_input_ids)
+    ref = m(input_ids=ids, labels=ids)
+    ref.loss.backward()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    loss, grads, logits = R.roberta_loss_and_grads(sd, ids, ids, cfg)
+    assert abs(loss.item() - ref.loss.item()) < 2e-5
+    assert torch.allclose(logits, ref.logits, atol=5e-5, rtol=1e-4)
+    for n, p in m.named_parameters():
+        if n in grads and p.grad is not None:
+            assert torch.allclose(grads[n], p.grad, atol=2e-6, rtol=2e-4), n
+
+
 def test_roberta_position_ids_rule(rgold):
     from oracle import roberta_oracle as R
 
