@@ -118,7 +118,7 @@ def cpu_reference_step_factory(model_name: str, sample_tokens: int):
             torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
             opt.step()
             model.zero_grad()
-            return float(loss)
+            return float(loss.detach())
 
         import transformers
 
@@ -144,6 +144,12 @@ def cpu_reference_step_factory(model_name: str, sample_tokens: int):
 
 
 def run_cpu_baseline(model_name: str, sample_tokens: int, steps: int, warmup: int) -> dict:
+    # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would otherwise make the
+    # reference arm at N > 1 a single-threaded (16x slower) run
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     step, kind, what = cpu_reference_step_factory(model_name, sample_tokens)
     for _ in range(warmup):
         step()

@@ -25,6 +25,18 @@ def test_reference_arm_json_line():
     assert "workload" in d["config"]
 
 
+def test_reference_arm_uses_all_cores_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 of the reference arm must still use every core it may run on."""
+    import os
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--model", "pythia-70m", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-tokens", "16"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stderr[-1500:]
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
+
+
 def test_reference_arm_other_ranks_exit_silently():
     import os
 
