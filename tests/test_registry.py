@@ -141,3 +141,34 @@ def test_analytic_training_days_with_b200_row():
     assert PEAK_TFLOPS["a100"] == {"bf16": 312.0, "tf32": 156.0} and ampere_or_newer_gpu("b200") and not ampere_or_newer_gpu("v100")
     with pytest.raises(NotImplementedError):
         estimate_training_days_from_flops(1, 8, "v100", mc)
+
+
+def test_registry_matches_the_live_reference_registry():
+    """When the reference checkout is present (this container, not the GPU box): every hyper-parameter property of every in-scope
+    model class equals what the reference's own src/models registry returns (src/models/__init__.py:240-296, pythia.py, roberta.py)."""
+    ref_root = Path("/root/reference")
+    if not (ref_root / "src" / "models" / "__init__.py").exists():
+        pytest.skip("reference checkout not present")
+    from typing import get_args
+
+    from multimodal_llm_pretraining_b200.models import PythiaT
+    from multimodal_llm_pretraining_b200.optim import B200Adam, B200AdamW
+
+    sys.path.insert(0, str(ref_root))
+    try:
+        from src.models import get_model_class as ref_get_model_class  # the reference's registry
+    finally:
+        sys.path.remove(str(ref_root))
+    attrs = ["batch_size", "training_steps", "mixed_precision", "optimizer_kwargs", "scheduler_type", "scheduler_kwargs", "max_grad_norm",
+             "hf_training_args", "fsdp_layers_to_wrap", "vocab_size", "sequence_length", "supports_activation_checkpointing", "supports_compilation"]
+    for name in list(get_args(PythiaT)) + ["roberta"]:
+        ref, ours = ref_get_model_class(name), get_model_class(name)
+        for a in attrs:
+            mine, theirs = getattr(ours, a), getattr(ref, a)
+            assert str(getattr(mine, "value", mine)) == str(getattr(theirs, "value", theirs)), (name, a, mine, theirs)
+        assert ours.optimizer is {torch.optim.Adam: B200Adam, torch.optim.AdamW: B200AdamW}[ref.optimizer], name
+    # the synthetic dataset: same constructor arguments, item keys, dtypes and shapes (src/benchmarking/data.py:8-21)
+    ref_ds = ref_get_model_class("pythia-70m").load_dummy_dataset(num_samples=8)
+    our_ds = get_model_class("pythia-70m").load_dummy_dataset(num_samples=8, seed=0)
+    assert len(ref_ds) == len(our_ds) == 8
+    assert {k: (v.dtype, v.shape) for k, v in ref_ds[0].items()} == {k: (v.dtype, v.shape) for k, v in our_ds[0].items()}
