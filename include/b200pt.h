@@ -23,11 +23,16 @@
 extern "C" {
 #endif
 
-#define B200PT_ABI_VERSION 7
+#define B200PT_ABI_VERSION 8
 
 typedef void* b200_stream_t; /* cudaStream_t */
 
 int b200_abi_version(void);
+/* 16-bit element type of the loaded library: 0 = bf16 (libb200pt.so), 1 = IEEE fp16 (libb200pt_fp16.so — the SAME sources and
+ * the SAME entry points compiled with -DB200_ELEM_FP16; wherever this header says "bf16" that build reads and writes fp16:
+ * the reference trains every Pythia but 1b and RoBERTa in fp16, src/models/pythia.py:33-41, src/models/roberta.py:29-30).
+ * fp32 statistics / gradients of parameters / optimizer state are the same in both. */
+int b200_elem_dtype(void);
 const char* b200_last_error(void);
 /* One-time per-process/device setup: resolves cuTensorMapEncodeTiled, raises dynamic-smem limits. Idempotent. */
 int b200_init(int device);
@@ -60,7 +65,8 @@ int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float* sin_tab, 
                          int inverse, b200_stream_t stream);
 
 /* ---------------------------------------------------------------- Embedding
- * out[t,:] = table[ids[t],:] (HF:modeling_gpt_neox.py:345). bwd: dtable[ids[t],:] += dout[t,:] in fp32. */
+ * out[t,:] = table[ids[t],:] (HF:modeling_gpt_neox.py:345). bwd: dtable[ids[t],:] += dout[t,:] in fp32.
+ * An id outside [0, vocab) traps the kernel with a message (torch raises a device-side assert); vocab <= 0 = unchecked. */
 int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int T, int h, int vocab,
                        b200_stream_t stream);
 int b200_embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int T, int h, int vocab,
@@ -71,7 +77,7 @@ int b200_embedding_bwd_padding(const int64_t* ids, const void* dout, float* dtab
                                b200_stream_t stream);
 /* out[t,:] = LN-less sum of up to three bf16 table rows (RoBERTa word + position + token-type,
  * HF:models/roberta/modeling_roberta.py:56-144); ids1/ids2 may be NULL. */
-int b200_embedding3_fwd(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1,
+int b200_embedding3_fwd(const int64_t* ids0, const void* table0, int vocab0, const int64_t* ids1, const void* table1,
                         const int64_t* ids2, const void* table2, void* out, int T, int h, b200_stream_t stream);
 
 /* RoBERTa position ids: pos = cumsum(ids != pad) * (ids != pad) + pad along each row
@@ -89,9 +95,13 @@ int b200_dropout(const void* x, const void* residual, void* out, size_t n, float
  * labels != ignore_index. logits bf16 [T, ld] (V valid columns) are overwritten IN PLACE by
  * dlogits = (softmax - onehot) / n_valid when write_grad != 0.  row_loss fp32 [T]; n_valid device int (output of
  * b200_count_valid); loss_out device fp32 scalar. */
-int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int* n_valid, b200_stream_t stream);
+/* b200_count_valid also validates: a label that is neither ignore_index nor in [0, V) traps the kernel with a message
+ * (torch's cross_entropy raises a device-side assert for it); V <= 0 disables the check.
+ * grad_scale_dev (nullable device fp32 scalar): dlogits are multiplied by it — the fp16 loss scale is applied HERE, where
+ * (softmax - onehot) / n_valid (~1e-5) would otherwise underflow the 16-bit gradient. */
+int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int V, int* n_valid, b200_stream_t stream);
 int b200_cross_entropy(void* logits, const int64_t* labels, float* row_loss, const int* n_valid, int T, int V,
-                       int64_t ld, int64_t ignore_index, int write_grad, b200_stream_t stream);
+                       int64_t ld, int64_t ignore_index, int write_grad, const float* grad_scale_dev, b200_stream_t stream);
 int b200_mean_loss(const float* row_loss, const int* n_valid, int T, float* loss_out, b200_stream_t stream);
 
 /* ---------------------------------------------------------------- Column sums (bias gradients)
@@ -137,7 +147,8 @@ int b200_gemm_bf16(const b200_gemm_args* args, b200_stream_t stream);
  * Replaces F.scaled_dot_product_attention(is_causal=True) (HF:integrations/sdpa_attention.py:92-101) and RoBERTa's
  * eager softmax attention (HF:models/roberta/modeling_roberta.py:162-187) with causal=0.
  * q,k,v,o,do,dq,dk,dv: bf16; token t = b*S+s, head hh element d at  ptr[t*row_stride + hh*head_stride + d].
- * lse, delta: fp32 [B, H, S].  D in {64, 128, 256}.  scale = head_dim^-0.5. */
+ * lse, delta: fp32 [B, H, S].  D in {64, 80, 128, 256} (80 = Pythia-2.8b: read through zero-padding 3-D tensor maps and
+ * computed as 128).  scale = head_dim^-0.5 of the REAL head_dim. */
 typedef struct b200_attn_args {
     int B, S, H, D;
     int causal;
@@ -192,12 +203,34 @@ typedef struct b200_adam_group {
 int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
                    const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group,
                    const int64_t* chunk_state, int n_chunks, const b200_adam_group* groups, int n_groups,
-                   const float* grad_scale_dev, int zero_grad, b200_stream_t stream);
-/* out[0] += sum(x[i]^2) (fp32 atomics over per-block partials). */
-int b200_sumsq(const float* x, size_t n, float* out, b200_stream_t stream);
-/* norm_out = sqrt(sumsq); coef_out = min(1, max_norm / (norm + 1e-6)) (torch.nn.utils.clip_grad_norm_ semantics);
- * max_norm <= 0 gives coef 1. */
-int b200_clip_coef(const float* sumsq, float max_norm, float* norm_out, float* coef_out, b200_stream_t stream);
+                   const float* grad_scale_dev, int zero_grad, const int* skip_flag_dev, int g_packed, b200_stream_t stream);
+/* skip_flag_dev (nullable device int): when *skip_flag_dev != 0 the step leaves p, m, v and the shadow untouched (an fp16
+ * overflow step, torch.amp.GradScaler.step semantics); g is still cleared when zero_grad != 0.
+ * g_packed != 0: g is a packed shard buffer indexed like m / v (chunk_state[c] + i) instead of the full flat gradient buffer —
+ * ZeRO-2 (src/train.py:172-181), where a rank only holds the reduced gradients of the slices it owns. */
+
+/* out[0] += sum(x[i]^2), DETERMINISTIC (fixed per-block partials into `workspace`, then a fixed-order final sum; no atomics):
+ * replicas holding identical gradients get bit-identical norms. workspace: b200_sumsq_workspace_bytes() bytes. */
+size_t b200_sumsq_workspace_bytes(void);
+int b200_sumsq(const float* x, size_t n, float* out, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+/* Same over the chunks of an optimizer chunk table (the slices a ZeRO rank owns): one block per chunk writes partials[c]
+ * (fp32 [n_chunks], caller-owned), then the fixed-order final sum is added to out[0]. */
+int b200_sumsq_chunks(const float* x, const int64_t* chunk_start, const int32_t* chunk_len, int n_chunks, float* out,
+                      float* partials, b200_stream_t stream);
+/* norm_out = sqrt(sumsq) / loss_scale; coef_out = min(1, max_norm / (norm + 1e-6)) / loss_scale
+ * (torch.nn.utils.clip_grad_norm_ semantics on the UNSCALED gradients; max_norm <= 0 gives min(..) = 1).
+ * loss_scale_dev (nullable) = the fp16 loss scale the gradients carry (NULL = 1).
+ * found_inf_out (nullable device int) = 1 when sumsq is inf / nan, i.e. some gradient overflowed (the overflow check of
+ * GradScaler.unscale_ / DeepSpeed has_overflow: a single non-finite element makes the sum non-finite), else 0. */
+int b200_clip_coef(const float* sumsq, float max_norm, const float* loss_scale_dev, float* norm_out, float* coef_out,
+                   int* found_inf_out, b200_stream_t stream);
+/* Dynamic loss scale, all state on the device (no host sync in the step): on overflow the hysteresis counter is decremented
+ * and, once spent (or hysteresis <= 1), scale = max(scale * backoff_factor, min_scale); after growth_interval consecutive
+ * clean steps scale *= growth_factor and the hysteresis is refilled. torch.amp.GradScaler = (2, 0.5, 2000, -, 1);
+ * the reference's DeepSpeed config (src/train.py:143-150) = (2, 0.5, 1000, min 1, hysteresis 2, initial 2^16). */
+int b200_loss_scale_update(float* scale, int* growth_tracker, int* hysteresis_left, const int* found_inf,
+                           float growth_factor, float backoff_factor, int growth_interval, float min_scale,
+                           int hysteresis, b200_stream_t stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200_stream_t stream);
 int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream);
 

@@ -1,4 +1,5 @@
-"""ctypes binding of libb200pt.so (the C ABI declared in include/b200pt.h).
+"""ctypes binding of libb200pt.so / libb200pt_fp16.so (the C ABI declared in include/b200pt.h; one build per 16-bit
+element type, same entry points).
 
 The library is the product: there is NO fallback. If it is missing, cannot be loaded, or the device is not sm_100,
 every op raises. PyTorch is used only for device memory and streams.
@@ -14,7 +15,8 @@ import torch
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["B200PT_LIB"]) if os.environ.get("B200PT_LIB") else _PKG / "libb200pt.so"  # override: kernel triage builds only
-ABI_VERSION = 7
+LIB_PATH_FP16 = _PKG / "libb200pt_fp16.so"
+ABI_VERSION = 8
 
 c_void_p, c_int, c_int64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
@@ -61,6 +63,7 @@ class AdamGroup(C.Structure):
 # name -> (restype, argtypes); the single source of truth for "every symbol include/b200pt.h declares"
 SIGNATURES = {
     "b200_abi_version": (c_int, []),
+    "b200_elem_dtype": (c_int, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_init": (c_int, [c_int]),
     "b200_layernorm_fwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_float, c_void_p]),
@@ -72,20 +75,23 @@ SIGNATURES = {
     "b200_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_embedding_bwd_padding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
-    "b200_embedding3_fwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_void_p]),
+    "b200_embedding3_fwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int, c_int, c_void_p]),
     "b200_roberta_position_ids": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "b200_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, C.c_uint64, c_void_p]),
-    "b200_count_valid": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
-    "b200_cross_entropy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "b200_count_valid": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p]),
+    "b200_cross_entropy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200_mean_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_colsum_workspace_bytes": (c_size_t, [c_int]),
     "b200_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b200_attention_fwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
     "b200_attention_bwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
-    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p]),
-    "b200_sumsq": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
-    "b200_clip_coef": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "b200_sumsq_workspace_bytes": (c_size_t, []),
+    "b200_sumsq": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200_sumsq_chunks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200_clip_coef": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200_loss_scale_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_int, c_void_p]),
     "b200_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_scale_f32": (c_int, [c_void_p, c_size_t, c_void_p, c_float, c_void_p]),
 }
@@ -95,50 +101,63 @@ class B200Error(RuntimeError):
     pass
 
 
-_lib = None
-_inited_devices: set[int] = set()
+_libs: dict[str, C.CDLL] = {}
+_inited_devices: set[tuple[str, int]] = set()
 
 
-def load() -> C.CDLL:
-    """dlopen libb200pt.so and bind every declared symbol. No compute, safe without a GPU."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+def _variant(dtype) -> str:
+    if dtype is None or dtype == torch.bfloat16 or dtype == "bf16":
+        return "bf16"
+    if dtype == torch.float16 or dtype == "fp16":
+        return "fp16"
+    raise B200Error(f"libb200pt is built for bf16 and fp16 tensors, not {dtype}")
+
+
+def load(dtype=None) -> C.CDLL:
+    """dlopen the library for `dtype` (bf16 default, fp16) and bind every declared symbol. No compute, safe without a GPU."""
+    var = _variant(dtype)
+    if var in _libs:
+        return _libs[var]
+    path = LIB_PATH if var == "bf16" else LIB_PATH_FP16
+    if not path.exists():
         raise B200Error(
-            f"{LIB_PATH} is missing: build it with `python -m multimodal_llm_pretraining_b200.csrc.build` "
+            f"{path} is missing: build it with `python -m multimodal_llm_pretraining_b200.csrc.build` "
             "(or __graft_entry__.build()). There is no fallback path."
         )
-    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_NOW if hasattr(os, "RTLD_NOW") else 2)
+    lib = C.CDLL(str(path), mode=os.RTLD_NOW if hasattr(os, "RTLD_NOW") else 2)  # RTLD_LOCAL: the two builds share symbol names
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
     got = lib.b200_abi_version()
     if got != ABI_VERSION:
-        raise B200Error(f"libb200pt ABI version {got} != expected {ABI_VERSION}: rebuild the library")
-    _lib = lib
+        raise B200Error(f"{path.name} ABI version {got} != expected {ABI_VERSION}: rebuild the library")
+    if lib.b200_elem_dtype() != (0 if var == "bf16" else 1):
+        raise B200Error(f"{path.name} reports element type {lib.b200_elem_dtype()}, expected the {var} build")
+    _libs[var] = lib
     return lib
 
 
-def lib_for(device: torch.device | int) -> C.CDLL:
-    """Library handle with b200_init done for `device`. Raises if no sm_100 GPU is present."""
-    lib = load()
+def lib_for(device: torch.device | int, dtype=None) -> C.CDLL:
+    """Library handle (for `dtype`) with b200_init done for `device`. Raises if no sm_100 GPU is present."""
+    var = _variant(dtype)
+    lib = load(var)
     idx = device if isinstance(device, int) else (device.index if device.index is not None else torch.cuda.current_device())
-    if idx not in _inited_devices:
+    if (var, idx) not in _inited_devices:
         if not torch.cuda.is_available():
             raise B200Error("libb200pt needs a CUDA device (sm_100a); none is available and there is no CPU fallback")
         with torch.cuda.device(idx):
             rc = lib.b200_init(idx)
         if rc != 0:
             raise B200Error(f"b200_init({idx}) failed: {lib.b200_last_error().decode()}")
-        _inited_devices.add(idx)
+        _inited_devices.add((var, idx))
     return lib
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, lib: C.CDLL | None = None) -> None:
     if rc != 0:
-        raise B200Error(f"{what} failed ({rc}): {load().b200_last_error().decode()}")
+        msgs = [l.b200_last_error().decode() for l in ([lib] if lib is not None else list(_libs.values()))]
+        raise B200Error(f"{what} failed ({rc}): {' | '.join(m for m in msgs if m)}")
 
 
 def stream_ptr() -> int:

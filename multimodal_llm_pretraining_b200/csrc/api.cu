@@ -43,6 +43,11 @@ int resolve_driver();  // gemm.cu
 }  // namespace b200
 
 extern "C" int b200_abi_version(void) { return B200PT_ABI_VERSION; }
+#ifdef B200_ELEM_FP16
+extern "C" int b200_elem_dtype(void) { return 1; }  // this build reads every 16-bit tensor as IEEE fp16
+#else
+extern "C" int b200_elem_dtype(void) { return 0; }  // bf16
+#endif
 extern "C" const char* b200_last_error(void) { return b200::err_buf(); }
 
 extern "C" int b200_init(int device) {

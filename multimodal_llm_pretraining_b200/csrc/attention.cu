@@ -51,25 +51,25 @@ struct AttnParams {
     int causal;
     float scale;
     int64_t qkv_head_stride;
-    __nv_bfloat16* o;
+    elem_t* o;
     int64_t o_row_stride, o_head_stride;
     float* lse;
     const float* delta;
-    __nv_bfloat16* dq;
-    __nv_bfloat16* dk;
-    __nv_bfloat16* dv;
+    elem_t* dq;
+    elem_t* dk;
+    elem_t* dv;
     int64_t dqkv_row_stride, dqkv_head_stride;
-    __nv_bfloat16* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
+    elem_t* p_out;   // dQ pass only (nullable): bf16 P and dS tiles are also written to [B*H, S, S] scratch so that
     int trace;
     // attention-probability dropout (RoBERTa, HF:models/roberta/modeling_roberta.py:209,236): keep iff hash16 >= drop_thr,
     // kept probabilities scaled by drop_scale = 65536 / (65536 - drop_thr); 0 = off. Generic kernels only.
     uint32_t drop_thr;
     float drop_scale;
     unsigned long long drop_seed;
-    const __nv_bfloat16* d_o;  // score pass: delta = rowsum(dO * O) is computed in its prologue (no separate pre-pass)
+    const elem_t* d_o;  // score pass: delta = rowsum(dO * O) is computed in its prologue (no separate pre-pass)
     int d_real;  // head_dim as stored (80 for Pythia-2.8b); the kernels run on D = d_real rounded up to 64/128/256 with the
     int pad3d;   // tail columns zero-filled by 3-D TMA maps {d, head, token} (pad3d = 1) and clipped again on store
-    __nv_bfloat16* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
+    elem_t* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
 };
 
 // Dropout mask of score element (q, k) of head bh: the 16-bit lane (q & 1) * 2 + (k & 1) of one 64-bit hash per 2 x 2 block of
@@ -209,8 +209,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // keeps descriptors in uniform registers and issues UTCHMMA back to back; a lane==0 branch costs ~17 instructions
         // of register->uniform broadcast per MMA, more than a 128x64x16 MMA takes to execute)
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, false, false);  // S = Q K^T: both K-major
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);    // O = P V  : V is MN-major (d contiguous)
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, BN, false, false);  // S = Q K^T: both K-major
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, D, false, true);    // O = P V  : V is MN-major (d contiguous)
             const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
             const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
             const uint64_t p_desc = umma_desc_sw128(smem_u32(sP), 16, 1024);
@@ -336,7 +336,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const float inv_l = l > 0.f ? 1.0f / l : 0.f;
         const bool row_ok = q_idx < p.S;
-        __nv_bfloat16* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
+        elem_t* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
             uint32_t v[32];
@@ -493,8 +493,8 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else if (warp == 5) {
         // ---------------------------------------------------------------- MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN, false, false);  // S = Q K^T (A = Q from TMEM)
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);    // O += P V (V MN-major)
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, BN, false, false);  // S = Q K^T (A = Q from TMEM)
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, D, false, true);    // O += P V (V MN-major)
             const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 8192, 1024);
             const uint64_t p_desc = umma_desc_sw128(smem_u32(sP), 16, 1024);
@@ -646,7 +646,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const float inv_l = l > 0.f ? 1.0f / l : 0.f;
         const bool tma_out = (p.S % 128) == 0;  // whole 128-row boxes: stage O in the (idle) K ring and TMA-store full lines
-        __nv_bfloat16* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
+        elem_t* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
 #pragma unroll 1
         for (int c = 0; c < D / 32; ++c) {
             uint32_t v[32];
@@ -689,7 +689,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =================================================================================================================
 // delta[b,h,s] = sum_d dO * O ; one warp per (token, head)
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+attn_delta_kernel(const elem_t* __restrict__ o, const elem_t* __restrict__ d_o, float* __restrict__ delta,
                   int B, int S, int H, int D, int64_t row_stride, int64_t head_stride) {
     pdl_prologue();
     const int lane = threadIdx.x & 31;
@@ -698,8 +698,8 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
          w += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
         const int hh = static_cast<int>(w % H);
         const int64_t t = w / H;
-        const __nv_bfloat16* op = o + t * row_stride + hh * head_stride;
-        const __nv_bfloat16* dp = d_o + t * row_stride + hh * head_stride;
+        const elem_t* op = o + t * row_stride + hh * head_stride;
+        const elem_t* dp = d_o + t * row_stride + hh * head_stride;
         float s = 0.f;
         for (int c = lane * 8; c < D; c += 256) {
             const uint4 a = ld_nc_v4(op + c), g = ld_nc_v4(dp + c);
@@ -849,8 +849,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
     } else if (warp == 5) {
         // ---------------------------------------------------------------- MMA issuer (one elected thread, polling)
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
-            constexpr uint32_t idesc_acc = umma_idesc_bf16(128, DKV ? DH : D, false, true);
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, BT, false, false);
+            constexpr uint32_t idesc_acc = umma_idesc_f16(128, DKV ? DH : D, false, true);
             const uint64_t r1_desc = umma_desc_sw128(smem_u32(sR1), 16, 1024);
             const uint64_t r2_desc = umma_desc_sw128(smem_u32(sR2), 16, 1024);
             const uint64_t t1k_desc0 = umma_desc_sw128(smem_u32(sT1), 16, 1024);    // streamed tiles as K-major B (scores)
@@ -1075,13 +1075,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
         constexpr int NOUT = DKV ? 2 : 1;
 #pragma unroll 1
         for (int which = 0; which < NOUT; ++which) {
-            __nv_bfloat16* base;
+            elem_t* base;
             float mul;
             uint32_t tcol;
             if (!DKV) base = p.dq, mul = p.scale, tcol = TM_ACC1;
             else if (which == 0) base = p.dv, mul = 1.0f, tcol = TM_ACC1;
             else base = p.dk, mul = p.scale, tcol = TM_ACC2;
-            __nv_bfloat16* orow = base + static_cast<size_t>(row_base + r_idx) * p.dqkv_row_stride +
+            elem_t* orow = base + static_cast<size_t>(row_base + r_idx) * p.dqkv_row_stride +
                                   static_cast<size_t>(h) * p.dqkv_head_stride + half * DH;
             constexpr int NC = (DKV ? DH : D) / 32;
 #pragma unroll 1
@@ -1260,8 +1260,8 @@ attn_bwd_dq256_kernel(const __grid_constant__ CUtensorMap tmDO, const __grid_con
     } else if (warp == 5) {
         // ---------------------------------------------------------------- MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, BT, false, false);
-            constexpr uint32_t idesc_dq = umma_idesc_bf16(128, D, false, true);
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, BT, false, false);
+            constexpr uint32_t idesc_dq = umma_idesc_f16(128, D, false, true);
             const uint64_t do_desc = umma_desc_sw128(smem_u32(sDO), 16, 1024);
             const uint64_t kk_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);    // K tile as K-major B (scores)
             const uint64_t km_desc0 = umma_desc_sw128(smem_u32(sK), 8192, 1024);  // K tile as MN-major B (dQ += dS K)
@@ -1513,19 +1513,19 @@ static AttnParams make_params(const b200_attn_args* a) {
     p.causal = a->causal;
     p.scale = a->scale;
     p.qkv_head_stride = a->qkv_head_stride;
-    p.o = static_cast<__nv_bfloat16*>(a->o);
+    p.o = static_cast<elem_t*>(a->o);
     p.o_row_stride = a->o_row_stride, p.o_head_stride = a->o_head_stride;
     p.lse = a->lse;
     p.delta = a->delta;
-    p.dq = static_cast<__nv_bfloat16*>(a->dq);
-    p.dk = static_cast<__nv_bfloat16*>(a->dk);
-    p.dv = static_cast<__nv_bfloat16*>(a->dv);
+    p.dq = static_cast<elem_t*>(a->dq);
+    p.dk = static_cast<elem_t*>(a->dk);
+    p.dv = static_cast<elem_t*>(a->dv);
     p.dqkv_row_stride = a->dqkv_row_stride, p.dqkv_head_stride = a->dqkv_head_stride;
     p.p_out = nullptr, p.ds_out = nullptr;
     p.drop_thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr);
     p.drop_seed = a->dropout_seed;
-    p.d_o = static_cast<const __nv_bfloat16*>(a->d_o);
+    p.d_o = static_cast<const elem_t*>(a->d_o);
     p.d_real = a->D;
     p.pad3d = padded_head(a) ? 1 : 0;
     static const int tr = getenv("B200_ATTN_TRACE") ? atoi(getenv("B200_ATTN_TRACE")) : 0;  // 1: first CTA, 2: a late CTA
@@ -1601,8 +1601,8 @@ static int launch_bwd_impl(const b200_attn_args* a, cudaStream_t st, bool store_
     dim3 grid(((a->S + 127) / 128) * (DKV ? D / DH : 1), a->H, a->B);
     AttnParams prm = make_params(a);
     if (store_scores) {
-        prm.p_out = static_cast<__nv_bfloat16*>(a->p_scratch);
-        prm.ds_out = static_cast<__nv_bfloat16*>(a->ds_scratch);
+        prm.p_out = static_cast<elem_t*>(a->p_scratch);
+        prm.ds_out = static_cast<elem_t*>(a->ds_scratch);
     }
     launch_k(kern, dim3(grid), dim3(192), L::TOTAL, st, r1, r2, t1, t2, prm);
     return check_launch(DKV ? "attention_bwd_dkv" : "attention_bwd_dq");
@@ -1685,15 +1685,13 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         // deep K/V rings wherever shared memory allows: a TMA load takes ~2000 clocks under load, a tile a few hundred
         case 64: {
             static const bool one_cta = getenv("B200_ATTN_FWD_1CTA") != nullptr;  // perf triage only
-            // 64-key blocks, two CTAs per SM. The dropout instantiation of that variant (168 registers, the cap two resident
-            // CTAs leave) raises an illegal-address fault about once per 10^4 CTAs — only with two CTAs resident (padding the
-            // dynamic smem to force one per SM: clean), independent of the mask values (keep-all still faults), and not when
-            // compiled to 96 registers (scripts/dev/stress_fwd64_drop.py; triage log in DESIGN.md §8). Its memory-instruction
-            // mix is identical to the dropout-free build, which has never faulted. Root cause open; dropout runs use the
-            // one-CTA layout (tests/test_roberta_gpu.py::test_full_depth_training_steps_with_dropout).
-            static const bool drop_2cta = getenv("B200_ATTN_FWD_DROP_2CTA") != nullptr;  // triage of that fault only
-            if (one_cta || (a->dropout_p > 0.f && !drop_2cta)) return launch_fwd<64, 128, 4>(a, st);
-            return launch_fwd<64, 64, 3>(a, st);
+            // Without dropout: 64-key blocks, two CTAs per SM. With dropout: the one-CTA layout (128-key blocks). The dropout
+            // instantiation of the two-CTA variant (168 registers) raised an illegal-address fault about once per 10^4 CTAs in
+            // round 1 (triage log in DESIGN.md); its cause was never found, so that instantiation is NOT built any more
+            // (attn_fwd_kernel<64, 64, 3, true> does not exist in the library) rather than shipped behind a switch.
+            if (a->dropout_p > 0.f) return launch_fwd_impl<64, 128, 4, true>(a, st);
+            if (one_cta) return launch_fwd_impl<64, 128, 4, false>(a, st);
+            return launch_fwd_impl<64, 64, 3, false>(a, st);
         }
         case 80:  // zero-padded to 128 by the 3-D tensor maps
         case 128: return launch_fwd<128, 128, 2>(a, st);
@@ -1718,7 +1716,7 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
         int64_t blocks = (total_warps + 7) / 8;
         const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
         if (blocks > cap) blocks = cap;
-        launch_k(attn_delta_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(a->o), static_cast<const __nv_bfloat16*>(a->d_o),
+        launch_k(attn_delta_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, static_cast<const elem_t*>(a->o), static_cast<const elem_t*>(a->d_o),
                                                                     a->delta, a->B, a->S, a->H, a->D, a->o_row_stride, a->o_head_stride);
         if ((rc = check_launch("attention_delta"))) return rc;
     }

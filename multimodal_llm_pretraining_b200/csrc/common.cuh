@@ -3,10 +3,29 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// The 16-bit element type of this build. libb200pt.so is compiled with elem_t = bf16; the SAME sources compiled with
+// -DB200_ELEM_FP16 give libb200pt_fp16.so, the identical C ABI over IEEE half tensors (the reference's precision for every
+// Pythia but 1b and for RoBERTa: src/models/pythia.py:33-41, src/models/roberta.py:29-30). Everything that converts goes
+// through the helpers below ("bf" in their names = "the build's 16-bit type"); tcgen05 kind::f16 takes either format through
+// the instruction descriptor, TMA through the tensor-map data type. Accumulation, statistics and optimizer state are fp32
+// in both builds.
+// ------------------------------------------------------------------------------------------------
+#ifdef B200_ELEM_FP16
+typedef __half elem_t;
+#define B200_TMAP_ELEM_TYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define B200_ELEM_DTYPE_ID 1
+#else
+typedef __nv_bfloat16 elem_t;
+#define B200_TMAP_ELEM_TYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define B200_ELEM_DTYPE_ID 0
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // small utilities
@@ -43,7 +62,16 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// bf16x2 <-> float2
+// packed pair of 16-bit elements <-> float2
+#ifdef B200_ELEM_FP16
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_to_f(elem_t v) { return __half2float(v); }
+__device__ __forceinline__ elem_t f_to_elem(float v) { return __float2half_rn(v); }
+#else
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
     float2 r;
     r.x = __uint_as_float(u << 16);
@@ -54,7 +82,9 @@ __device__ __forceinline__ uint32_t f2_to_bf2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float bf_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float bf_to_f(elem_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ elem_t f_to_elem(float v) { return __float2bfloat16_rn(v); }
+#endif
 
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
     uint4 r;
@@ -247,9 +277,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= 2ull << 61;
     return d;
 }
-// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+// Instruction descriptor for kind::f16 with elem_t inputs (A/B format field: 0 = fp16, 1 = bf16) and fp32 accumulation.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    constexpr uint32_t ab_fmt = B200_ELEM_DTYPE_ID == 0 ? 1u : 0u;
+    return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.

@@ -59,14 +59,14 @@ __device__ __forceinline__ float block_reduce_sum_n(float v, float* sm) {
 }
 
 __global__ void __launch_bounds__(CE_THREADS)
-ce_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
-          const int* __restrict__ n_valid, int V, int64_t ld, int64_t ignore_index, int write_grad) {
+ce_kernel(elem_t* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
+          const int* __restrict__ n_valid, int V, int64_t ld, int64_t ignore_index, int write_grad, const float* __restrict__ grad_scale) {
     pdl_prologue();
     __shared__ float sm[CE_THREADS / 32];
     __shared__ float s_xlabel;
     const int row = blockIdx.x;
     const int64_t label = labels[row];
-    __nv_bfloat16* rp = logits + static_cast<size_t>(row) * ld;
+    elem_t* rp = logits + static_cast<size_t>(row) * ld;
     const int n_vec = static_cast<int>(ld / 8);
     const bool ignored = (label == ignore_index);
 
@@ -118,7 +118,7 @@ ce_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels
     if (threadIdx.x == 0) row_loss[row] = lse - s_xlabel;
     if (!write_grad) return;
     const int nv = *n_valid;
-    const float inv_n = 1.0f / static_cast<float>(nv > 0 ? nv : 1);
+    const float inv_n = (grad_scale ? *grad_scale : 1.0f) / static_cast<float>(nv > 0 ? nv : 1);
     const float lses = lse * LOG2E;
 #pragma unroll
     for (int i = 0; i < CE_NV; ++i) {
@@ -159,13 +159,14 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, 
 constexpr int CE2_THREADS = 512;
 
 __global__ void __launch_bounds__(CE2_THREADS, 2)
-ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
-               const int* __restrict__ n_valid, int T, int V, int64_t ld, int64_t ignore_index, int write_grad) {
+ce_smem_kernel(elem_t* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
+               const int* __restrict__ n_valid, int T, int V, int64_t ld, int64_t ignore_index, int write_grad,
+               const float* __restrict__ grad_scale) {
     pdl_prologue();
     extern __shared__ __align__(16) uint8_t ce_smem[];
     __shared__ float sm[CE2_THREADS / 32];
     __shared__ uint64_t bar;
-    __nv_bfloat16* srow = reinterpret_cast<__nv_bfloat16*>(ce_smem);
+    elem_t* srow = reinterpret_cast<elem_t*>(ce_smem);
     const int n_vec = static_cast<int>(ld / 8);
     const int v_vec = V / 8;          // vectors that are entirely valid
     const uint32_t row_bytes = static_cast<uint32_t>(ld * 2);
@@ -175,11 +176,13 @@ ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ l
         fence_barrier_init();
     }
     __syncthreads();
-    const float inv_n = write_grad ? 1.0f / static_cast<float>(max(*n_valid, 1)) : 0.f;
+    // grad_scale: the fp16 loss scale is folded into dlogits HERE — (softmax - onehot) / n_valid is ~1e-5 and would be flushed
+    // to zero / subnormal in fp16 if the scale were applied only by the consumer GEMMs
+    const float inv_n = write_grad ? (grad_scale ? *grad_scale : 1.0f) / static_cast<float>(max(*n_valid, 1)) : 0.f;
     uint32_t phase = 0;
     for (int row = blockIdx.x; row < T; row += gridDim.x) {
         const int64_t label = labels[row];
-        __nv_bfloat16* rp = logits + static_cast<size_t>(row) * ld;
+        elem_t* rp = logits + static_cast<size_t>(row) * ld;
         const bool ignored = (label == ignore_index);
         if (threadIdx.x == 0) {
             tma_store_wait_read<0>();  // the previous row's bulk store has finished reading the buffer
@@ -285,11 +288,22 @@ ce_smem_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ l
     if (threadIdx.x == 0) tma_store_wait_all<0>();
 }
 
-__global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* __restrict__ labels, int T, int64_t ignore_index, int* out) {
+// Also validates the labels (it scans every one anyway): a label that is neither ignore_index nor inside [0, V) would index
+// outside the logits row. torch's cross_entropy raises a device-side assert for it; so does this (message + trap).
+__global__ void __launch_bounds__(1024) count_valid_kernel(const int64_t* __restrict__ labels, int T, int64_t ignore_index, int V, int* out) {
     pdl_prologue();
     __shared__ int sm[32];
     int c = 0;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) c += (labels[i] != ignore_index);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const int64_t l = labels[i];
+        if (l != ignore_index) {
+            ++c;
+            if (V > 0 && (l < 0 || l >= V)) {
+                printf("b200pt cross_entropy: label %lld at position %d is outside [0, %d) and is not ignore_index\n", (long long)l, i, V);
+                __trap();
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
@@ -323,13 +337,13 @@ __global__ void __launch_bounds__(1024) mean_loss_kernel(const float* __restrict
 
 using namespace b200;
 
-extern "C" int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int* n_valid, b200_stream_t stream) {
+extern "C" int b200_count_valid(const int64_t* labels, int T, int64_t ignore_index, int V, int* n_valid, b200_stream_t stream) {
     B200_REQUIRE(T > 0, "count_valid: T must be positive");
-    launch_k(count_valid_kernel, dim3(1), dim3(1024), 0, as_stream(stream), labels, T, ignore_index, n_valid);
+    launch_k(count_valid_kernel, dim3(1), dim3(1024), 0, as_stream(stream), labels, T, ignore_index, V, n_valid);
     return check_launch("count_valid");
 }
 extern "C" int b200_cross_entropy(void* logits, const int64_t* labels, float* row_loss, const int* n_valid, int T, int V,
-                                  int64_t ld, int64_t ignore_index, int write_grad, b200_stream_t stream) {
+                                  int64_t ld, int64_t ignore_index, int write_grad, const float* grad_scale_dev, b200_stream_t stream) {
     B200_REQUIRE(T > 0 && V > 0 && ld >= V && ld % 8 == 0, "cross_entropy: need ld >= V and ld %% 8 == 0 (V=%d ld=%lld)", V, (long long)ld);
     B200_REQUIRE(aligned16(logits), "cross_entropy: logits must be 16B aligned");
     static const bool old_path = getenv("B200_CE_OLD") != nullptr;  // perf triage only
@@ -344,12 +358,12 @@ extern "C" int b200_cross_entropy(void* logits, const int64_t* labels, float* ro
         const int per_sm = row_bytes <= 110 * 1024 ? 2 : 1;  // two rows per SM when they fit next to each other
         int grid = num_sms() * per_sm;
         if (grid > T) grid = T;
-        launch_k(ce_smem_kernel, dim3(grid), dim3(CE2_THREADS), row_bytes, as_stream(stream), static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, T, V, ld,
-                                                                            ignore_index, write_grad);
+        launch_k(ce_smem_kernel, dim3(grid), dim3(CE2_THREADS), row_bytes, as_stream(stream), static_cast<elem_t*>(logits), labels, row_loss, n_valid, T, V, ld,
+                                                                            ignore_index, write_grad, grad_scale_dev);
         return check_launch("cross_entropy");
     }
     B200_REQUIRE(ld <= static_cast<int64_t>(CE_THREADS) * CE_NV * 8, "cross_entropy: ld %lld > %d unsupported", (long long)ld, CE_THREADS * CE_NV * 8);
-    launch_k(ce_kernel, dim3(T), dim3(CE_THREADS), 0, as_stream(stream), static_cast<__nv_bfloat16*>(logits), labels, row_loss, n_valid, V, ld, ignore_index, write_grad);
+    launch_k(ce_kernel, dim3(T), dim3(CE_THREADS), 0, as_stream(stream), static_cast<elem_t*>(logits), labels, row_loss, n_valid, V, ld, ignore_index, write_grad, grad_scale_dev);
     return check_launch("cross_entropy");
 }
 extern "C" int b200_mean_loss(const float* row_loss, const int* n_valid, int T, float* loss_out, b200_stream_t stream) {

@@ -53,7 +53,7 @@ gelu_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4
 // One thread handles one (token, head, which in {q,k}, pair-of-8) : 8 low dims [i0,i0+8) and their partners at +rot/2.
 // When rot/2 is not a multiple of 8 (e.g. rot=20 for pythia-2.8b) falls back to a scalar pair-per-thread kernel.
 __global__ void __launch_bounds__(256)
-rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+rope_vec_kernel(elem_t* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                 int T, int S, int nh, int hd, int half, int inverse) {
     pdl_prologue();
     const int vec_per = half / 8;  // vectors per (token, head, q|k)
@@ -67,7 +67,7 @@ rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t
         const int head = static_cast<int>(r % nh);
         const int t = static_cast<int>(r / nh);
         const int pos = t % S;
-        __nv_bfloat16* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + vi * 8;
+        elem_t* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + vi * 8;
         const uint4 lo = *reinterpret_cast<const uint4*>(base);
         const uint4 hi = *reinterpret_cast<const uint4*>(base + half);
         const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -91,7 +91,7 @@ rope_vec_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t
     }
 }
 __global__ void __launch_bounds__(256)
-rope_scalar_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+rope_scalar_kernel(elem_t* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                    int T, int S, int nh, int hd, int half, int inverse) {
     pdl_prologue();
     const size_t total = static_cast<size_t>(T) * nh * 2 * half;
@@ -104,31 +104,35 @@ rope_scalar_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ co
         const int head = static_cast<int>(r % nh);
         const int t = static_cast<int>(r / nh);
         const int pos = t % S;
-        __nv_bfloat16* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + i;
+        elem_t* base = qkv + (static_cast<size_t>(t) * nh + head) * 3 * hd + which * hd + i;
         const float a = bf_to_f(base[0]), b = bf_to_f(base[half]);
         const float c = cos_tab[static_cast<size_t>(pos) * half + i];
         float s = sin_tab[static_cast<size_t>(pos) * half + i];
         if (inverse) s = -s;
-        base[0] = __float2bfloat16_rn(a * c - b * s);
-        base[half] = __float2bfloat16_rn(b * c + a * s);
+        base[0] = f_to_elem(a * c - b * s);
+        base[half] = f_to_elem(b * c + a * s);
     }
 }
 
 // ----------------------------------------------------------------------------------------------- Embedding
 // one warp per token row; 16-byte vectors
 __global__ void __launch_bounds__(256)
-embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __restrict__ t0,
-                     const int64_t* __restrict__ ids1, const __nv_bfloat16* __restrict__ t1,
-                     const int64_t* __restrict__ ids2, const __nv_bfloat16* __restrict__ t2,
-                     __nv_bfloat16* __restrict__ out, int T, int h) {
+embedding_fwd_kernel(const int64_t* __restrict__ ids0, const elem_t* __restrict__ t0,
+                     const int64_t* __restrict__ ids1, const elem_t* __restrict__ t1,
+                     const int64_t* __restrict__ ids2, const elem_t* __restrict__ t2,
+                     elem_t* __restrict__ out, int T, int h, int vocab0) {
     pdl_prologue();
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
-        const __nv_bfloat16* r0 = t0 + static_cast<size_t>(ids0[t]) * h;
-        const __nv_bfloat16* r1 = ids1 ? t1 + static_cast<size_t>(ids1[t]) * h : nullptr;
-        const __nv_bfloat16* r2 = ids2 ? t2 + static_cast<size_t>(ids2[t]) * h : nullptr;
-        __nv_bfloat16* o = out + static_cast<size_t>(t) * h;
+        if (vocab0 > 0 && (ids0[t] < 0 || ids0[t] >= vocab0)) {  // torch's embedding raises a device-side assert here
+            if (lane == 0) printf("b200pt embedding: token id %lld at position %d is outside [0, %d)\n", (long long)ids0[t], t, vocab0);
+            __trap();
+        }
+        const elem_t* r0 = t0 + static_cast<size_t>(ids0[t]) * h;
+        const elem_t* r1 = ids1 ? t1 + static_cast<size_t>(ids1[t]) * h : nullptr;
+        const elem_t* r2 = ids2 ? t2 + static_cast<size_t>(ids2[t]) * h : nullptr;
+        elem_t* o = out + static_cast<size_t>(t) * h;
         for (int c = lane * 8; c < h; c += 256) {
             uint4 v = *reinterpret_cast<const uint4*>(r0 + c);
             if (r1 || r2) {
@@ -165,7 +169,7 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids0, const __nv_bfloat16* __re
 }
 // scatter-add into fp32 table gradient. Random ids over a 50k vocab rarely collide, so plain fp32 REDs are cheap.
 __global__ void __launch_bounds__(256)
-embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dout, float* __restrict__ dtable,
+embedding_bwd_kernel(const int64_t* __restrict__ ids, const elem_t* __restrict__ dout, float* __restrict__ dtable,
                      int T, int h, int64_t skip_id) {
     pdl_prologue();
     const int warps_per_block = blockDim.x >> 5;
@@ -174,7 +178,7 @@ embedding_bwd_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __res
         const int64_t id = ids[t];
         if (id == skip_id) continue;  // nn.Embedding(padding_idx=...): the padding row receives no gradient
         float* drow = dtable + static_cast<size_t>(id) * h;
-        const __nv_bfloat16* g = dout + static_cast<size_t>(t) * h;
+        const elem_t* g = dout + static_cast<size_t>(t) * h;
         for (int c = lane * 8; c < h; c += 256) {
             const uint4 v = ld_nc_v4(g + c);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -198,10 +202,10 @@ cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, si
         dst[i] = make_uint2(f2_to_bf2(v.x, v.y), f2_to_bf2(v.z, v.w));
     }
 }
-__global__ void cast_f32_bf16_tail(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t start, size_t n) {
+__global__ void cast_f32_bf16_tail(const float* __restrict__ src, elem_t* __restrict__ dst, size_t start, size_t n) {
     pdl_prologue();
     const size_t i = start + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+    if (i < n) dst[i] = f_to_elem(src[i]);
 }
 __global__ void __launch_bounds__(256)
 scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scale_dev, float scale_host) {
@@ -216,7 +220,7 @@ scale_f32_kernel(float* __restrict__ x, size_t n, const float* __restrict__ scal
 // ----------------------------------------------------------------------------------------------- column sums (bias grads)
 // partial[rc][c] = sum over rows of chunk rc of x[r][c]; block = 32 column-lanes (8 cols each) x 8 row-lanes.
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int64_t ld, int rows_per_chunk,
+colsum_partial_kernel(const elem_t* __restrict__ x, int rows, int cols, int64_t ld, int rows_per_chunk,
                       float* __restrict__ partial) {
     pdl_prologue();
     __shared__ float sm[8][32][9];
@@ -351,7 +355,7 @@ extern "C" int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float
     B200_REQUIRE(rot > 0 && rot % 2 == 0 && rot <= hd, "rope: rot (%d) must be even and <= head_dim (%d)", rot, hd);
     const int half = rot / 2;
     const int T = B * S;
-    auto p = static_cast<__nv_bfloat16*>(qkv);
+    auto p = static_cast<elem_t*>(qkv);
     if (half % 8 == 0 && hd % 8 == 0 && aligned16(qkv)) {
         const size_t total = static_cast<size_t>(T) * nh * 2 * (half / 8);
         launch_k(rope_vec_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, as_stream(stream), p, cos_tab, sin_tab, T, S, nh, hd, half, inverse);
@@ -362,34 +366,37 @@ extern "C" int b200_rope_qk_inplace(void* qkv, const float* cos_tab, const float
     return check_launch("rope_qk_inplace");
 }
 
-extern "C" int b200_embedding3_fwd(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1,
-                                   const int64_t* ids2, const void* table2, void* out, int T, int h,
-                                   b200_stream_t stream) {
+static int embedding_fwd_impl(const int64_t* ids0, const void* table0, const int64_t* ids1, const void* table1, const int64_t* ids2,
+                              const void* table2, void* out, int T, int h, int vocab0, b200_stream_t stream) {
     B200_REQUIRE(h % 8 == 0 && aligned16(table0) && aligned16(out), "embedding_fwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    launch_k(embedding_fwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), 
-        ids0, static_cast<const __nv_bfloat16*>(table0), ids1, static_cast<const __nv_bfloat16*>(table1), ids2,
-        static_cast<const __nv_bfloat16*>(table2), static_cast<__nv_bfloat16*>(out), T, h);
+    launch_k(embedding_fwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream),
+        ids0, static_cast<const elem_t*>(table0), ids1, static_cast<const elem_t*>(table1), ids2,
+        static_cast<const elem_t*>(table2), static_cast<elem_t*>(out), T, h, vocab0);
     return check_launch("embedding_fwd");
+}
+extern "C" int b200_embedding3_fwd(const int64_t* ids0, const void* table0, int vocab0, const int64_t* ids1, const void* table1,
+                                   const int64_t* ids2, const void* table2, void* out, int T, int h,
+                                   b200_stream_t stream) {
+    return embedding_fwd_impl(ids0, table0, ids1, table1, ids2, table2, out, T, h, vocab0, stream);
 }
 extern "C" int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int T, int h, int vocab,
                                   b200_stream_t stream) {
-    (void)vocab;
-    return b200_embedding3_fwd(ids, table, nullptr, nullptr, nullptr, nullptr, out, T, h, stream);
+    return embedding_fwd_impl(ids, table, nullptr, nullptr, nullptr, nullptr, out, T, h, vocab, stream);
 }
 extern "C" int b200_embedding_bwd(const int64_t* ids, const void* dout, float* dtable, int T, int h, int vocab,
                                   b200_stream_t stream) {
     (void)vocab;
     B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, -1);
+    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const elem_t*>(dout), dtable, T, h, -1);
     return check_launch("embedding_bwd");
 }
 extern "C" int b200_embedding_bwd_padding(const int64_t* ids, const void* dout, float* dtable, int T, int h, int64_t padding_idx,
                                           b200_stream_t stream) {
     B200_REQUIRE(h % 8 == 0 && aligned16(dout), "embedding_bwd: h must be a multiple of 8, pointers 16B aligned");
     const int blocks = ew_grid(static_cast<size_t>(T) * 32, 256);
-    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const __nv_bfloat16*>(dout), dtable, T, h, padding_idx);
+    launch_k(embedding_bwd_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids, static_cast<const elem_t*>(dout), dtable, T, h, padding_idx);
     return check_launch("embedding_bwd_padding");
 }
 
@@ -397,7 +404,7 @@ extern "C" int b200_cast_f32_to_bf16(const float* src, void* dst, size_t n, b200
     B200_REQUIRE(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0, "cast: src must be 16B and dst 8B aligned");
     const size_t n4 = n / 4;
     if (n4) launch_k(cast_f32_bf16_kernel, dim3(ew_grid(n4, 256)), dim3(256), 0, as_stream(stream), reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n4);
-    if (n % 4) launch_k(cast_f32_bf16_tail, dim3(1), dim3(32), 0, as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), n4 * 4, n);
+    if (n % 4) launch_k(cast_f32_bf16_tail, dim3(1), dim3(32), 0, as_stream(stream), src, static_cast<elem_t*>(dst), n4 * 4, n);
     return check_launch("cast_f32_to_bf16");
 }
 extern "C" int b200_scale_f32(float* x, size_t n, const float* scale_dev, float scale_host, b200_stream_t stream) {
@@ -418,7 +425,7 @@ extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, f
     const int rows_per_chunk = (rows + chunks - 1) / chunks;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
     float* part = static_cast<float*>(workspace);
-    launch_k(colsum_partial_kernel, dim3(col_blocks, chunks), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(x), rows, cols, ld, rows_per_chunk, part);
+    launch_k(colsum_partial_kernel, dim3(col_blocks, chunks), dim3(256), 0, as_stream(stream), static_cast<const elem_t*>(x), rows, cols, ld, rows_per_chunk, part);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
     launch_k(colsum_finalize_kernel, dim3((cols + 255) / 256), dim3(256), 0, as_stream(stream), part, chunks, cols, out);

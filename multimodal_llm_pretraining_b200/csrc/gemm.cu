@@ -38,12 +38,12 @@ struct GemmParams {
     int c_fp32;
     int accumulate;
     const float* bias;
-    const __nv_bfloat16* residual;
+    const elem_t* residual;
     int64_t ldr;
     int gelu;
     const float* alpha_dev;
-    __nv_bfloat16* aux_out;
-    const __nv_bfloat16* dgelu_in;
+    elem_t* aux_out;
+    const elem_t* dgelu_in;
     int tiles_m, tiles_n;
     int tma_store;  // bf16 output without accumulate: stage 128x64 slabs in smem and TMA-store them (full-line writes)
     // batched mode: problem z = zb * zH + zh adds (zb * x_b + zh * x_h) to the TMA coordinate x of each operand
@@ -151,7 +151,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 *reinterpret_cast<float4*>(c + 4) = make_float4(x[4], x[5], x[6], x[7]);
             }
         } else {
-            __nv_bfloat16* c = static_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col;
+            elem_t* c = static_cast<elem_t*>(p.C) + static_cast<size_t>(row) * p.ldc + col;
             if (p.accumulate) {
                 const uint4 cv = *reinterpret_cast<const uint4*>(c);
                 const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
@@ -318,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // The loop body must cost fewer issue cycles than the 4 x 128 tensor cycles it feeds: descriptors are advanced
         // by adding (byte offset >> 4) to precomputed 64-bit templates, and nothing in the loop is warp-collective.
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN, A_MN, B_MN);
             const uint64_t adesc0 = A_MN ? umma_desc_sw128(smem_u32(sA), SLICE_BYTES, 1024) : umma_desc_sw128(smem_u32(sA), 16, 1024);
             const uint64_t bdesc0 = B_MN ? umma_desc_sw128(smem_u32(sB), SLICE_BYTES, 1024) : umma_desc_sw128(smem_u32(sB), 16, 1024);
             constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
@@ -515,7 +515,7 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t 
     cuuint64_t strides[1] = {pitch_elems * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(m, B200_TMAP_ELEM_TYPE, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu box=%ux%u", (int)r,
@@ -542,7 +542,7 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1,
     cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
     cuuint32_t box[3] = {box0, 1, box2};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(m, B200_TMAP_ELEM_TYPE, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
@@ -652,12 +652,12 @@ static void fill_params(const b200_gemm_args* a, GemmParams& p) {
     p.M = a->M, p.N = a->N, p.K = a->K;
     p.C = a->C, p.ldc = a->ldc, p.c_fp32 = a->c_fp32, p.accumulate = a->accumulate;
     p.bias = a->bias;
-    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.residual = static_cast<const elem_t*>(a->residual);
     p.ldr = a->ldr;
     p.gelu = a->gelu;
     p.alpha_dev = a->alpha_dev;
-    p.aux_out = static_cast<__nv_bfloat16*>(a->aux_out);
-    p.dgelu_in = static_cast<const __nv_bfloat16*>(a->dgelu_in);
+    p.aux_out = static_cast<elem_t*>(a->aux_out);
+    p.dgelu_in = static_cast<const elem_t*>(a->dgelu_in);
     p.Z = 1, p.zH = 1;
     p.alpha_host = 1.0f;
     p.split_k = 1;

@@ -27,9 +27,9 @@ __device__ __forceinline__ float group_sum(float v, int G, float* red) {
 
 template <int NV>
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
-              __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
-              __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+ln_fwd_kernel(const elem_t* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
+              elem_t* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
+              elem_t* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
               int cols, float eps, int G) {
     pdl_prologue();
     __shared__ float red[4];
@@ -132,9 +132,9 @@ __device__ __forceinline__ float group_sum_bar(float v, int G, float* red, int g
 
 template <int NV, int NA>
 __global__ void __launch_bounds__(256)
-ln_fwd_persist_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
-                      __nv_bfloat16* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
-                      __nv_bfloat16* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+ln_fwd_persist_kernel(const elem_t* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
+                      elem_t* __restrict__ y1, const float* __restrict__ g2, const float* __restrict__ b2,
+                      elem_t* __restrict__ y2, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
                       int cols, float eps, int G) {
     pdl_prologue();
     __shared__ float red[8];
@@ -227,10 +227,10 @@ ln_fwd_persist_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
 // ---------------------------------------------------------------------------------------------------------------
 template <int NV, int NA>
 __global__ void __launch_bounds__(256, 1)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-              const float* __restrict__ g1, const __nv_bfloat16* __restrict__ dy1, const float* __restrict__ g2,
-              const __nv_bfloat16* __restrict__ dy2, const __nv_bfloat16* __restrict__ dres,
-              __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int rows, int cols, int G) {
+ln_bwd_kernel(const elem_t* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const float* __restrict__ g1, const elem_t* __restrict__ dy1, const float* __restrict__ g2,
+              const elem_t* __restrict__ dy2, const elem_t* __restrict__ dres,
+              elem_t* __restrict__ dx, float* __restrict__ partial, int rows, int cols, int G) {
     pdl_prologue();
     __shared__ float red[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -408,9 +408,9 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
     B200_REQUIRE(cols <= 8192, "layernorm_fwd: cols %d > 8192 unsupported", cols);
     B200_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm_fwd: pointers must be 16-byte aligned");
     B200_REQUIRE((gamma2 == nullptr) == (y2 == nullptr) && (gamma2 == nullptr) == (beta2 == nullptr), "layernorm_fwd: gamma2/beta2/y2 must be all set or all NULL");
-    auto xs = static_cast<const __nv_bfloat16*>(x);
-    auto y1s = static_cast<__nv_bfloat16*>(y);
-    auto y2s = static_cast<__nv_bfloat16*>(y2);
+    auto xs = static_cast<const elem_t*>(x);
+    auto y1s = static_cast<elem_t*>(y);
+    auto y2s = static_cast<elem_t*>(y2);
     cudaStream_t st = as_stream(stream);
     // G warps per row: 4 up to 3072 columns (<= 3 vectors per lane keeps the register-resident parameters small), else 8
     const int G = cols <= 3072 ? 4 : 8;
@@ -455,11 +455,11 @@ extern "C" int b200_layernorm_bwd(const void* x, const float* mean, const float*
     int grid = num_sms();
     const int max_blocks = (rows + rows_per_block - 1) / rows_per_block;
     if (grid > max_blocks) grid = max_blocks;
-    auto xs = static_cast<const __nv_bfloat16*>(x);
-    auto d1 = static_cast<const __nv_bfloat16*>(dy);
-    auto d2 = static_cast<const __nv_bfloat16*>(dy2);
-    auto dr = static_cast<const __nv_bfloat16*>(dres);
-    auto dxs = static_cast<__nv_bfloat16*>(dx);
+    auto xs = static_cast<const elem_t*>(x);
+    auto d1 = static_cast<const elem_t*>(dy);
+    auto d2 = static_cast<const elem_t*>(dy2);
+    auto dr = static_cast<const elem_t*>(dres);
+    auto dxs = static_cast<elem_t*>(dx);
     float* part = static_cast<float*>(workspace);
     cudaStream_t st = as_stream(stream);
 #define LAUNCH(NVV, NAA) launch_k(ln_bwd_kernel<NVV, NAA>, dim3(grid), dim3(256), 0, st, xs, mean, rstd, gamma, d1, gamma2, d2, dr, dxs, part, rows, cols, G)

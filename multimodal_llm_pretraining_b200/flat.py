@@ -4,6 +4,7 @@ HBM layout (one contiguous buffer each, same offsets in all of them):
     master : fp32   — the nn.Parameters are views into it (HF-compatible state_dict, torch optimizers work on it)
     grad   : fp32   — the .grad of every parameter is a view into it; wgrad GEMMs accumulate straight into it
     shadow : bf16   — what the tensor-core kernels read; rewritten by the fused Adam in the same pass that updates master
+             (fp16 after set_compute_dtype(torch.float16): the reference's precision for every Pythia but 1b and RoBERTa)
 Every parameter starts at a multiple of 64 elements (256 B fp32 / 128 B bf16) so TMA bases and vector accesses are aligned.
 A contiguous layout makes the optimizer one launch, the gradient norm one launch, and DDP / ZeRO-1 collectives plain
 slices of one buffer (bucket = a contiguous range, shard = a contiguous range).
@@ -20,7 +21,7 @@ ALIGN = 64
 
 
 class FlatParams:
-    def __init__(self, shapes: list[tuple], device="cpu"):
+    def __init__(self, shapes: list[tuple], device="cpu", compute_dtype: torch.dtype = torch.bfloat16):
         """shapes: (name, shape) or (name, shape, alloc_shape): alloc_shape >= shape reserves zero padding behind the
         parameter (e.g. RoBERTa's 50265-row vocabulary padded to 50304 rows so that the tied decoder GEMM, its wgrad and
         the cross entropy run on 16-byte-aligned rows); the nn.Parameter and state_dict see `shape` only."""
@@ -36,7 +37,8 @@ class FlatParams:
         self.numel = (off + 8 * ALIGN - 1) // (8 * ALIGN) * (8 * ALIGN)
         self.master = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.grad = torch.zeros(self.numel, dtype=torch.float32, device=device)
-        self.shadow = torch.zeros(self.numel, dtype=torch.bfloat16, device=device)
+        self.compute_dtype = compute_dtype
+        self.shadow = torch.zeros(self.numel, dtype=compute_dtype, device=device)
         self.shadow_version = -1
         self.params: list[nn.Parameter] = []
         self.pending_grad_scale: torch.Tensor | None = None  # clip coefficient folded into the next fused Adam step
@@ -44,6 +46,31 @@ class FlatParams:
         # are current; `master_consolidator` (a collective) refreshes the rest of the master on demand
         self.master_stale = False
         self.master_consolidator = None
+        # ZeRO-2 (engine.py): there is no full gradient buffer (`grad` is None); `grad_router(name)` returns the transient
+        # bucket buffer (and the offset inside it) the gradient of `name` is accumulated into during the current backward,
+        # `grad_zero_fn()` clears the rank's shard accumulator
+        self.grad_router = None
+        self.grad_zero_fn = None
+
+    # ---- gradient views (through the router when the engine shards gradients)
+    def _gbuf(self, name: str) -> tuple[torch.Tensor, int]:
+        if self.grad_router is not None:
+            return self.grad_router(name)
+        return self.grad, self.offsets[name]
+
+    def gview(self, name: str) -> torch.Tensor:
+        buf, o = self._gbuf(name)
+        s = self.shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def gview_alloc(self, name: str) -> torch.Tensor:
+        buf, o = self._gbuf(name)
+        s = self.alloc_shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def gview_span(self, first: str, shape: tuple[int, ...]) -> torch.Tensor:
+        buf, o = self._gbuf(first)
+        return buf[o:o + math.prod(shape)].view(shape)
 
     # ---- views
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -69,7 +96,7 @@ class FlatParams:
 
     def make_parameter(self, name: str) -> nn.Parameter:
         p = nn.Parameter(self.view(self.master, name), requires_grad=True)
-        p.grad = self.view(self.grad, name)
+        p.grad = self.view(self.grad, name) if self.grad is not None else None
         p._b200_flat = (self, self.offsets[name], math.prod(self.shapes[name]))  # type: ignore[attr-defined]
         self.params.append(p)
         return p
@@ -77,7 +104,7 @@ class FlatParams:
     def rebind(self, params: dict[str, nn.Parameter]) -> None:
         for name, p in params.items():
             p.data = self.view(self.master, name)
-            p.grad = self.view(self.grad, name)
+            p.grad = self.view(self.grad, name) if self.grad is not None else None
             p._b200_flat = (self, self.offsets[name], math.prod(self.shapes[name]))  # type: ignore[attr-defined]
 
     def apply(self, fn) -> None:
@@ -87,9 +114,19 @@ class FlatParams:
             raise TypeError("B200 modules keep fp32 master parameters; bf16 compute copies are managed internally "
                             "(do not call .half()/.bfloat16() on the module)")
         self.master = new_master.contiguous()
-        self.grad = self.grad.to(device=self.master.device)
+        if self.grad is not None:
+            self.grad = self.grad.to(device=self.master.device)
         self.shadow = self.shadow.to(device=self.master.device)
         self.shadow_version = -1
+
+    def set_compute_dtype(self, dtype: torch.dtype) -> None:
+        """bf16 (default) or fp16: re-allocates the 16-bit compute copy; the next forward re-casts it from the master."""
+        if dtype not in (torch.bfloat16, torch.float16):
+            raise TypeError(f"compute dtype must be torch.bfloat16 or torch.float16, not {dtype}")
+        if dtype != self.compute_dtype:
+            self.compute_dtype = dtype
+            self.shadow = torch.zeros(self.numel, dtype=dtype, device=self.master.device)
+            self.shadow_version = -1
 
     def consolidate(self) -> None:
         if self.master_stale and self.master_consolidator is not None:
@@ -118,5 +155,8 @@ class FlatParams:
             self.shadow_version = v
 
     def zero_grad(self) -> None:
-        self.grad.zero_()
+        if self.grad is not None:
+            self.grad.zero_()
+        elif self.grad_zero_fn is not None:
+            self.grad_zero_fn()
         self.pending_grad_scale = None

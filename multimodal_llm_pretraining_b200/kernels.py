@@ -15,6 +15,8 @@ from . import _lib
 from ._lib import AdamGroup, AttnArgs, GemmArgs, check, ptr, stream_ptr
 
 BF16 = torch.bfloat16
+FP16 = torch.float16
+HALF = (BF16, FP16)  # 16-bit element types: libb200pt.so / libb200pt_fp16.so (same entry points, see include/b200pt.h)
 F32 = torch.float32
 
 # number of libb200pt kernel launches issued through this module (bench.py reports it as `gpu_launches`)
@@ -29,7 +31,8 @@ def _count(n: int) -> None:
 
 
 def _L(t: torch.Tensor):
-    return _lib.lib_for(t.device)
+    """Library for the tensor's device and 16-bit element type (fp32-only ops run from the bf16 build)."""
+    return _lib.lib_for(t.device, t.dtype if t.dtype in HALF else None)
 
 
 def _req(cond: bool, msg: str) -> None:
@@ -40,7 +43,7 @@ def _req(cond: bool, msg: str) -> None:
 # ----------------------------------------------------------------------------------------------------- LayerNorm
 def layernorm_fwd(x, gamma, beta, eps, gamma2=None, beta2=None):
     """x bf16 [rows, cols] -> (y, y2|None, mean, rstd)."""
-    _req(x.dtype == BF16 and x.is_contiguous() and x.dim() == 2, "layernorm_fwd: x must be contiguous bf16 [rows, cols]")
+    _req(x.dtype in HALF and x.is_contiguous() and x.dim() == 2, "layernorm_fwd: x must be contiguous bf16/fp16 [rows, cols]")
     _req(gamma.dtype == F32 and beta.dtype == F32, "layernorm_fwd: gamma/beta must be fp32")
     rows, cols = x.shape
     y = torch.empty_like(x)
@@ -68,7 +71,7 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 def layernorm_bwd(x, mean, rstd, gamma, dy, dgamma, dbeta, gamma2=None, dy2=None, dgamma2=None, dbeta2=None, dres=None):
     """Returns dx (bf16). dgamma/dbeta (fp32) are accumulated in place."""
     rows, cols = x.shape
-    _req(dy.dtype == BF16 and dy.is_contiguous() and dy.shape == x.shape, "layernorm_bwd: dy must match x")
+    _req(dy.dtype == x.dtype and x.dtype in HALF and dy.is_contiguous() and dy.shape == x.shape, "layernorm_bwd: dy must match x")
     _req(dgamma.dtype == F32 and dbeta.dtype == F32, "layernorm_bwd: dgamma/dbeta must be fp32")
     lib = _L(x)
     na = 2 if gamma2 is not None else 1
@@ -84,7 +87,7 @@ def layernorm_bwd(x, mean, rstd, gamma, dy, dgamma, dbeta, gamma2=None, dy2=None
 
 # ----------------------------------------------------------------------------------------------------- GELU / RoPE
 def gelu_fwd(x):
-    _req(x.dtype == BF16 and x.is_contiguous(), "gelu_fwd: contiguous bf16 expected")
+    _req(x.dtype in HALF and x.is_contiguous(), "gelu_fwd: contiguous bf16/fp16 expected")
     y = torch.empty_like(x)
     check(_L(x).b200_gelu_fwd(ptr(x), ptr(y), x.numel(), stream_ptr()), "b200_gelu_fwd")
     _count(1)
@@ -92,7 +95,7 @@ def gelu_fwd(x):
 
 
 def gelu_bwd(x, dy):
-    _req(x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous(), "gelu_bwd: contiguous bf16 expected")
+    _req(x.dtype in HALF and dy.dtype == x.dtype and x.is_contiguous() and dy.is_contiguous(), "gelu_bwd: contiguous bf16/fp16 expected")
     dx = torch.empty_like(x)
     check(_L(x).b200_gelu_bwd(ptr(x), ptr(dy), ptr(dx), x.numel(), stream_ptr()), "b200_gelu_bwd")
     _count(1)
@@ -101,7 +104,7 @@ def gelu_bwd(x, dy):
 
 def rope_qk_inplace(qkv, cos, sin, B, S, nh, hd, rot, inverse=False):
     """qkv bf16 [B*S, nh*3*hd] packed per head as [q|k|v]; cos/sin fp32 [S, rot/2]."""
-    _req(qkv.dtype == BF16 and qkv.is_contiguous() and qkv.numel() == B * S * nh * 3 * hd, "rope: bad qkv")
+    _req(qkv.dtype in HALF and qkv.is_contiguous() and qkv.numel() == B * S * nh * 3 * hd, "rope: bad qkv")
     _req(cos.dtype == F32 and sin.dtype == F32 and cos.is_contiguous() and sin.is_contiguous(), "rope: cos/sin must be fp32")
     _req(cos.shape[0] >= S and cos.shape[1] == rot // 2, "rope: cos/sin must be [>=S, rot/2]")
     check(_L(qkv).b200_rope_qk_inplace(ptr(qkv), ptr(cos), ptr(sin), B, S, nh, hd, rot, int(inverse), stream_ptr()), "b200_rope_qk_inplace")
@@ -112,9 +115,9 @@ def rope_qk_inplace(qkv, cos, sin, B, S, nh, hd, rot, inverse=False):
 # ----------------------------------------------------------------------------------------------------- Embedding
 def embedding_fwd(ids, table):
     _req(ids.dtype == torch.int64 and ids.is_contiguous(), "embedding_fwd: ids must be contiguous int64")
-    _req(table.dtype == BF16 and table.is_contiguous(), "embedding_fwd: table must be contiguous bf16")
+    _req(table.dtype in HALF and table.is_contiguous(), "embedding_fwd: table must be contiguous bf16/fp16")
     T, h = ids.numel(), table.shape[1]
-    out = torch.empty(T, h, dtype=BF16, device=table.device)
+    out = torch.empty(T, h, dtype=table.dtype, device=table.device)
     check(_L(table).b200_embedding_fwd(ptr(ids), ptr(table), ptr(out), T, h, table.shape[0], stream_ptr()), "b200_embedding_fwd")
     _count(1)
     return out
@@ -122,15 +125,16 @@ def embedding_fwd(ids, table):
 
 def embedding3_fwd(ids0, table0, ids1=None, table1=None, ids2=None, table2=None):
     T, h = ids0.numel(), table0.shape[1]
-    out = torch.empty(T, h, dtype=BF16, device=table0.device)
-    check(_L(table0).b200_embedding3_fwd(ptr(ids0), ptr(table0), ptr(ids1), ptr(table1), ptr(ids2), ptr(table2), ptr(out), T, h, stream_ptr()), "b200_embedding3_fwd")
+    _req(table0.dtype in HALF and all(t is None or t.dtype == table0.dtype for t in (table1, table2)), "embedding3_fwd: tables must share a 16-bit dtype")
+    out = torch.empty(T, h, dtype=table0.dtype, device=table0.device)
+    check(_L(table0).b200_embedding3_fwd(ptr(ids0), ptr(table0), table0.shape[0], ptr(ids1), ptr(table1), ptr(ids2), ptr(table2), ptr(out), T, h, stream_ptr()), "b200_embedding3_fwd")
     _count(1)
     return out
 
 
 def embedding_bwd(ids, dout, dtable, padding_idx=None):
     """dtable[ids[t]] += dout[t] (fp32 atomics); rows with ids == padding_idx are skipped (nn.Embedding padding_idx)."""
-    _req(dout.dtype == BF16 and dout.is_contiguous() and dtable.dtype == F32, "embedding_bwd: dout bf16, dtable fp32")
+    _req(dout.dtype in HALF and dout.is_contiguous() and dtable.dtype == F32, "embedding_bwd: dout bf16/fp16, dtable fp32")
     T, h = ids.numel(), dtable.shape[1]
     if padding_idx is None:
         check(_L(dout).b200_embedding_bwd(ptr(ids), ptr(dout), ptr(dtable), T, h, dtable.shape[0], stream_ptr()), "b200_embedding_bwd")
@@ -150,8 +154,8 @@ def roberta_position_ids(ids, pad_id: int):
 
 def dropout(x, p: float, seed: int, residual=None, out=None):
     """out = dropout(x) (+ residual), mask = f(seed, element index); call again on the gradient with the same seed for backward."""
-    _req(x.dtype == BF16 and x.is_contiguous() and x.numel() % 8 == 0, "dropout: contiguous bf16 with numel % 8 == 0")
-    _req(residual is None or (residual.dtype == BF16 and residual.is_contiguous() and residual.numel() == x.numel()), "dropout: bad residual")
+    _req(x.dtype in HALF and x.is_contiguous() and x.numel() % 8 == 0, "dropout: contiguous bf16/fp16 with numel % 8 == 0")
+    _req(residual is None or (residual.dtype == x.dtype and residual.is_contiguous() and residual.numel() == x.numel()), "dropout: bad residual")
     out = torch.empty_like(x) if out is None else out
     check(_L(x).b200_dropout(ptr(x), ptr(residual), ptr(out), x.numel(), float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, stream_ptr()), "b200_dropout")
     _count(1)
@@ -159,9 +163,12 @@ def dropout(x, p: float, seed: int, residual=None, out=None):
 
 
 # ----------------------------------------------------------------------------------------------------- Cross entropy
-def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
-    """logits bf16 [T, ld] (overwritten by dlogits/n_valid when write_grad). Returns (loss scalar fp32 tensor, n_valid int tensor)."""
-    _req(logits.dtype == BF16 and logits.dim() == 2 and logits.stride(1) == 1, "cross_entropy: logits must be bf16 [T, ld]")
+def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True, grad_scale=None):
+    """logits bf16/fp16 [T, ld] (overwritten by dlogits/n_valid when write_grad). Returns (loss scalar fp32 tensor, n_valid int tensor).
+    grad_scale (device fp32 scalar, optional): multiplied into dlogits — the fp16 loss scale. Labels outside [0, V) that are
+    not ignore_index trap the kernel (torch raises a device-side assert for them)."""
+    _req(logits.dtype in HALF and logits.dim() == 2 and logits.stride(1) == 1, "cross_entropy: logits must be bf16/fp16 [T, ld]")
+    _req(grad_scale is None or (grad_scale.dtype == F32 and grad_scale.numel() == 1), "cross_entropy: grad_scale must be a device fp32 scalar")
     _req(labels.dtype == torch.int64 and labels.is_contiguous(), "cross_entropy: labels must be contiguous int64")
     T, ld = logits.shape[0], logits.stride(0)
     V = logits.shape[1] if V is None else V
@@ -171,9 +178,9 @@ def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
     row_loss = torch.empty(T, dtype=F32, device=dev)
     loss = torch.empty((), dtype=F32, device=dev)
     s = stream_ptr()
-    check(lib.b200_count_valid(ptr(labels), T, ignore_index, ptr(n_valid), s), "b200_count_valid")
+    check(lib.b200_count_valid(ptr(labels), T, ignore_index, V, ptr(n_valid), s), "b200_count_valid")
     _count(1)
-    check(lib.b200_cross_entropy(ptr(logits), ptr(labels), ptr(row_loss), ptr(n_valid), T, V, ld, ignore_index, int(write_grad), s), "b200_cross_entropy")
+    check(lib.b200_cross_entropy(ptr(logits), ptr(labels), ptr(row_loss), ptr(n_valid), T, V, ld, ignore_index, int(write_grad), ptr(grad_scale), s), "b200_cross_entropy")
     _count(1)
     check(lib.b200_mean_loss(ptr(row_loss), ptr(n_valid), T, ptr(loss), s), "b200_mean_loss")
     _count(1)
@@ -182,7 +189,7 @@ def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True):
 
 def colsum_(x, out):
     """out[c] (fp32) += sum_r x[r, c] for bf16 x [rows, cols]."""
-    _req(x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.numel() == x.shape[1], "colsum: bad tensors")
+    _req(x.dtype in HALF and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.numel() == x.shape[1], "colsum: bad tensors")
     lib = _L(x)
     rows, cols = x.shape
     ws = _workspace(x.device, lib.b200_colsum_workspace_bytes(cols))
@@ -192,10 +199,12 @@ def colsum_(x, out):
 
 
 # ----------------------------------------------------------------------------------------------------- GEMM
-def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=False, bias=None, residual=None,
+def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=None, accumulate=False, bias=None, residual=None,
          gelu=False, alpha=None, aux_out=None, dgelu_in=None):
     """C[M,N] = epi(alpha * A·Bᵀ).  A is [M,K] (a_mn=False) or [K,M] (a_mn=True); B is [N,K] or [K,N] (b_mn=True)."""
-    _req(A.dtype == BF16 and B.dtype == BF16 and A.dim() == 2 and B.dim() == 2, "gemm: A,B must be 2-D bf16")
+    _req(A.dtype in HALF and B.dtype == A.dtype and A.dim() == 2 and B.dim() == 2, "gemm: A,B must be 2-D bf16 (or both fp16)")
+    E = A.dtype
+    out_dtype = E if out_dtype is None else out_dtype
     _req(A.stride(1) == 1 and B.stride(1) == 1, "gemm: A,B must have unit inner stride")
     if a_mn:
         K, M = A.shape
@@ -209,7 +218,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=F
     if out is None:
         _req(not accumulate, "gemm: accumulate needs out")
         out = torch.empty(M, N, dtype=out_dtype, device=A.device)
-    _req(out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (BF16, F32), "gemm: bad out")
+    _req(out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (E, F32), "gemm: bad out")
     a = GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.A, a.lda, a.a_mn = ptr(A), A.stride(0), int(a_mn)
@@ -220,10 +229,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=F
         a.bias = ptr(bias)
     ldr = 0
     if residual is not None:
-        _req(residual.dtype == BF16 and residual.shape == (M, N) and residual.stride(1) == 1, "gemm: bad residual")
+        _req(residual.dtype == E and residual.shape == (M, N) and residual.stride(1) == 1, "gemm: bad residual")
         a.residual, ldr = ptr(residual), residual.stride(0)
     if dgelu_in is not None:
-        _req(dgelu_in.dtype == BF16 and dgelu_in.shape == (M, N) and dgelu_in.stride(1) == 1, "gemm: bad dgelu_in")
+        _req(dgelu_in.dtype == E and dgelu_in.shape == (M, N) and dgelu_in.stride(1) == 1, "gemm: bad dgelu_in")
         _req(residual is None or residual.stride(0) == dgelu_in.stride(0), "gemm: residual and dgelu_in must share a pitch")
         a.dgelu_in, ldr = ptr(dgelu_in), dgelu_in.stride(0)
     a.ldr = ldr
@@ -232,7 +241,7 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=BF16, accumulate=F
         _req(alpha.dtype == F32 and alpha.numel() == 1, "gemm: alpha must be a device fp32 scalar")
         a.alpha_dev = ptr(alpha)
     if aux_out is not None:
-        _req(aux_out.dtype == BF16 and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0) and out.dtype == BF16, "gemm: aux_out must match a bf16 out")
+        _req(aux_out.dtype == E and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0) and out.dtype == E, "gemm: aux_out must match a 16-bit out")
         a.aux_out = ptr(aux_out)
     prof = GEMM_PROFILE
     if prof is not None:
@@ -253,12 +262,12 @@ def _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale):
     a.causal = int(causal)
     a.scale = float(scale)
     for t in (q, k, v):
-        _req(t.dtype == BF16 and t.dim() == 4 and t.shape == (B, S, H, D) and t.stride(3) == 1, "attention: q,k,v must be bf16 views [B,S,H,D] with unit inner stride")
+        _req(t.dtype in HALF and t.dtype == q.dtype and t.dim() == 4 and t.shape == (B, S, H, D) and t.stride(3) == 1, "attention: q,k,v must be bf16/fp16 views [B,S,H,D] with unit inner stride")
         _req(t.stride(0) == S * t.stride(1), "attention: batch stride must equal S * token stride")
         _req(t.stride(1) == q.stride(1) and t.stride(2) == q.stride(2), "attention: q,k,v must share strides")
     a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
     a.qkv_row_stride, a.qkv_head_stride = q.stride(1), q.stride(2)
-    _req(o.dtype == BF16 and o.shape == (B, S, H, D) and o.stride(3) == 1 and o.stride(0) == S * o.stride(1), "attention: bad o")
+    _req(o.dtype == q.dtype and o.shape == (B, S, H, D) and o.stride(3) == 1 and o.stride(0) == S * o.stride(1), "attention: bad o")
     a.o, a.o_row_stride, a.o_head_stride = ptr(o), o.stride(1), o.stride(2)
     _req(lse.dtype == F32 and lse.shape == (B, H, S) and lse.is_contiguous(), "attention: lse must be fp32 [B,H,S]")
     a.lse = ptr(lse)
@@ -269,12 +278,12 @@ USE_SCORE_SCRATCH = True
 _score_cache: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
 
 
-def _score_scratch(device, Z: int, S: int):
+def _score_scratch(device, Z: int, S: int, dtype=BF16):
     """Persistent bf16 [Z, S, S] P and dS scratch for the head_dim-256 backward (reused by every layer and step)."""
-    key = (device.index, torch.cuda.current_stream().cuda_stream, Z, S)
+    key = (device.index, torch.cuda.current_stream().cuda_stream, Z, S, dtype)
     if key not in _score_cache:
         _score_cache.clear()  # one shape at a time: these are GB-sized
-        _score_cache[key] = (torch.empty(Z, S, S, dtype=BF16, device=device), torch.empty(Z, S, S, dtype=BF16, device=device))
+        _score_cache[key] = (torch.empty(Z, S, S, dtype=dtype, device=device), torch.empty(Z, S, S, dtype=dtype, device=device))
     return _score_cache[key]
 
 
@@ -283,7 +292,7 @@ def attention_fwd(q, k, v, causal, scale=None, dropout_p: float = 0.0, dropout_s
     dropout_p > 0 drops softmax probabilities with the counter-based mask of (dropout_seed, head, query, key)."""
     B, S, H, D = q.shape
     scale = D ** -0.5 if scale is None else scale
-    o = torch.empty(B, S, H, D, dtype=BF16, device=q.device)
+    o = torch.empty(B, S, H, D, dtype=q.dtype, device=q.device)
     lse = torch.empty(B, H, S, dtype=F32, device=q.device)
     a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
     a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
@@ -299,16 +308,16 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None, dropout_
     scale = D ** -0.5 if scale is None else scale
     a = _attn_args(q, k, v, o, lse, B, S, H, D, causal, scale)
     a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF
-    _req(d_o.dtype == BF16 and d_o.shape == o.shape and d_o.stride() == o.stride(), "attention_bwd: dO must match O")
+    _req(d_o.dtype == q.dtype and d_o.shape == o.shape and d_o.stride() == o.stride(), "attention_bwd: dO must match O")
     for t in (dq, dk, dv):
-        _req(t.dtype == BF16 and t.shape == (B, S, H, D) and t.stride(3) == 1 and t.stride(0) == S * t.stride(1), "attention_bwd: bad dq/dk/dv")
+        _req(t.dtype == q.dtype and t.shape == (B, S, H, D) and t.stride(3) == 1 and t.stride(0) == S * t.stride(1), "attention_bwd: bad dq/dk/dv")
         _req(t.stride(1) == dq.stride(1) and t.stride(2) == dq.stride(2), "attention_bwd: dq,dk,dv must share strides")
     delta = torch.empty(B, H, S, dtype=F32, device=q.device)
     a.d_o, a.delta = ptr(d_o), ptr(delta)
     n_launch = 3
     if D == 256 and S % 256 == 0 and USE_SCORE_SCRATCH and dropout_p == 0.0:
         # head_dim 256: P / dS tiles go through HBM scratch and dK / dV become batched GEMMs (b200pt.h, b200_attn_args)
-        ps, dss = _score_scratch(q.device, B * H, S)
+        ps, dss = _score_scratch(q.device, B * H, S, q.dtype)
         a.p_scratch, a.ds_scratch = ptr(ps), ptr(dss)
         n_launch = 4
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
@@ -320,37 +329,69 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None, dropout_
 
 # ----------------------------------------------------------------------------------------------------- Optimizer
 def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_group, groups, grad_scale=None, zero_grad=False,
-              chunk_state=None):
+              chunk_state=None, skip_flag=None, g_packed=False):
+    """p_bf16: the 16-bit compute copy (bf16 or fp16; its dtype selects the library build). skip_flag (device int32, optional):
+    non-zero leaves p, m, v untouched (fp16 overflow step). g_packed: g is a packed shard buffer indexed like m / v (ZeRO-2)."""
     n_chunks = chunk_start.numel()
     arr = (AdamGroup * len(groups))()
     for i, gdict in enumerate(groups):
         arr[i].lr, arr[i].beta1, arr[i].beta2, arr[i].eps = gdict["lr"], gdict["beta1"], gdict["beta2"], gdict["eps"]
         arr[i].weight_decay, arr[i].bias_corr1, arr[i].bias_corr2 = gdict["weight_decay"], gdict["bias_corr1"], gdict["bias_corr2"]
         arr[i].adamw_mode = int(gdict["adamw_mode"])
-    check(_L(p).b200_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), int(state_base), ptr(chunk_start), ptr(chunk_len),
-                               ptr(chunk_group), ptr(chunk_state), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad), stream_ptr()), "b200_adam_step")
+    lib = _L(p_bf16) if p_bf16 is not None else _L(p)
+    check(lib.b200_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), int(state_base), ptr(chunk_start), ptr(chunk_len),
+                             ptr(chunk_group), ptr(chunk_state), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad),
+                             ptr(skip_flag), int(g_packed), stream_ptr()), "b200_adam_step")
     _count(1)
 
 
 def sumsq_(x, out):
-    """out (fp32 scalar tensor) += sum(x^2)."""
+    """out (fp32 scalar tensor) += sum(x^2); deterministic (fixed-order two-pass reduction, no atomics)."""
     _req(x.dtype == F32 and x.is_contiguous() and out.dtype == F32, "sumsq: fp32 expected")
-    check(_L(x).b200_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()), "b200_sumsq")
-    _count(1)
+    lib = _L(x)
+    ws = _workspace(x.device, lib.b200_sumsq_workspace_bytes())
+    check(lib.b200_sumsq(ptr(x), x.numel(), ptr(out), ptr(ws), ws.numel(), stream_ptr()), "b200_sumsq")
+    _count(2)
     return out
 
 
-def clip_coef(sumsq, max_norm):
+def sumsq_chunks_(x, chunk_start, chunk_len, out, partials=None):
+    """out += sum of squares of x over the chunks (chunk_start int64, chunk_len int32 device arrays): the slices a ZeRO rank owns."""
+    _req(x.dtype == F32 and x.is_contiguous() and out.dtype == F32, "sumsq_chunks: fp32 expected")
+    n = chunk_start.numel()
+    if partials is None or partials.numel() < n:
+        partials = torch.empty(max(n, 1), dtype=F32, device=x.device)
+    check(_L(x).b200_sumsq_chunks(ptr(x), ptr(chunk_start), ptr(chunk_len), n, ptr(out), ptr(partials), stream_ptr()), "b200_sumsq_chunks")
+    _count(2)
+    return out
+
+
+def clip_coef(sumsq, max_norm, loss_scale=None, found_inf=None):
+    """(norm, coef): norm = sqrt(sumsq) / loss_scale, coef = min(1, max_norm / (norm + 1e-6)) / loss_scale. found_inf (device
+    int32, optional) receives 1 when sumsq is inf / nan."""
     norm = torch.empty((), dtype=F32, device=sumsq.device)
     coef = torch.empty((), dtype=F32, device=sumsq.device)
-    check(_L(sumsq).b200_clip_coef(ptr(sumsq), float(max_norm), ptr(norm), ptr(coef), stream_ptr()), "b200_clip_coef")
+    check(_L(sumsq).b200_clip_coef(ptr(sumsq), float(max_norm if max_norm is not None else 0.0), ptr(loss_scale), ptr(norm), ptr(coef),
+                                   ptr(found_inf), stream_ptr()), "b200_clip_coef")
     _count(1)
     return norm, coef
 
 
+def loss_scale_update(scale, growth_tracker, hysteresis_left, found_inf, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000,
+                      min_scale=1.0, hysteresis=1):
+    """Device-side dynamic loss-scale update (b200pt.h: b200_loss_scale_update)."""
+    _req(scale.dtype == F32 and growth_tracker.dtype == torch.int32 and hysteresis_left.dtype == torch.int32 and found_inf.dtype == torch.int32,
+         "loss_scale_update: scale fp32, counters / flag int32")
+    check(_L(scale).b200_loss_scale_update(ptr(scale), ptr(growth_tracker), ptr(hysteresis_left), ptr(found_inf), float(growth_factor),
+                                           float(backoff_factor), int(growth_interval), float(min_scale), int(hysteresis), stream_ptr()),
+          "b200_loss_scale_update")
+    _count(1)
+
+
 def cast_f32_to_bf16(src, dst):
-    _req(src.dtype == F32 and dst.dtype == BF16 and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous(), "cast: bad tensors")
-    check(_L(src).b200_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "b200_cast_f32_to_bf16")
+    """dst (bf16 or fp16, selects the library build) = cast(src fp32)."""
+    _req(src.dtype == F32 and dst.dtype in HALF and src.numel() == dst.numel() and src.is_contiguous() and dst.is_contiguous(), "cast: bad tensors")
+    check(_L(dst).b200_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream_ptr()), "b200_cast_f32_to_bf16")
     _count(1)
     return dst
 

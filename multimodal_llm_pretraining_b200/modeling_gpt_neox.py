@@ -82,6 +82,19 @@ class _FlatModule(nn.Module):
             self._rope_cache = {}
         return self
 
+    # ---- precision: bf16 (default) or fp16 + loss scaling (src/models/pythia.py:33-41: fp16 for every Pythia but 1b)
+    loss_scale: torch.Tensor | None = None  # device fp32 scalar set by the engine's LossScaler in fp16 runs
+
+    @property
+    def compute_dtype(self) -> torch.dtype:
+        return self.flat.compute_dtype
+
+    def set_compute_dtype(self, dtype: torch.dtype) -> None:
+        """torch.bfloat16 or torch.float16: selects libb200pt.so / libb200pt_fp16.so for every kernel of this module. fp16
+        needs a loss scale (engine.LossScaler sets `loss_scale`; the cross entropy folds it into dlogits, the optimizer's
+        clip coefficient divides it out again)."""
+        self.flat.set_compute_dtype(dtype)
+
     def zero_grad(self, set_to_none: bool = False) -> None:  # grads are persistent views; "None" means zero here
         self.flat.zero_grad()
         self._ensure_grads_attached()
@@ -93,20 +106,36 @@ class _FlatModule(nn.Module):
         return super().state_dict(*args, **kwargs)
 
     def _ensure_grads_attached(self) -> None:
+        if self.flat.grad is None:  # ZeRO-2: gradients live in transient bucket buffers / the engine's shard accumulator
+            return
         for name, p in self.named_parameters():
             if p.grad is None:
                 p.grad = self.flat.view(self.flat.grad, name)
 
     def _grads_were_dropped(self) -> bool:
         """A foreign zero_grad(set_to_none=True) (torch optimizers, nn.Module default) drops the views: treat as zero."""
+        if self.flat.grad is None:
+            return False
         p = next(self.parameters())
         return p.grad is None
+
+    # engine hooks: grad_ready_hook(start, end) fires in backward as each bucket's gradients complete; param_wait_hook(start,
+    # end) is called in forward right before the parameters of a bucket are first read (ZeRO: the bucket's all-gather, which
+    # runs on a side stream, must have landed)
+    grad_ready_hook = None
+    param_wait_hook = None
+
+    def _wait_bucket(self, rng: tuple[int, int]) -> None:
+        if self.param_wait_hook is not None:
+            self.param_wait_hook(*rng)
 
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """Fused replacement for torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
         (src/benchmarking/utils.py:66-70): one sum-of-squares pass over the flat grad buffer; the clip coefficient stays
         on the device and is folded into the next B200Adam.step(). Returns the total norm (device scalar)."""
         f = self.flat
+        if f.grad is None:
+            raise RuntimeError("gradients are sharded by the TrainEngine (ZeRO-2): clipping happens in manual_optimization_step")
         sumsq = torch.zeros((), dtype=torch.float32, device=f.grad.device)
         K.sumsq_(f.grad, sumsq)
         norm, coef = K.clip_coef(sumsq, max_norm)
@@ -169,6 +198,8 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         self.embed_out = _Params(f, "embed_out", ("weight",))
         self.gradient_checkpointing = False
         self.grad_ready_hook = None  # callable(start, end) on flat-grad element ranges, fired in backward order
+        self.param_wait_hook = None
+        self._layer_ranges = [self._layer_range(i) for i in range(self.L)]
         self._rope_cache: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}
         self.reset_parameters()
 
@@ -229,7 +260,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         return self.flat.view(self.flat.master, name)
 
     def _g(self, name: str) -> torch.Tensor:  # fp32 gradient accumulator
-        return self.flat.view(self.flat.grad, name)
+        return self.flat.gview(name)
 
     def _rope_tables(self, S: int, device) -> tuple[torch.Tensor, torch.Tensor]:
         key = (S, device)
@@ -254,7 +285,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         o, lse = K.attention_fwd(qkv5[:, :, :, 0], qkv5[:, :, :, 1], qkv5[:, :, :, 2], causal=True, scale=hd ** -0.5)
         o2 = o.view(B * S, h)
         att = K.gemm(o2, self._w(f"{p}.attention.dense.weight"), bias=self._p(f"{p}.attention.dense.bias"), residual=x)
-        h1 = torch.empty(B * S, self.inter, dtype=BF16, device=x.device) if keep else None
+        h1 = torch.empty(B * S, self.inter, dtype=x.dtype, device=x.device) if keep else None
         g = K.gemm(a2, self._w(f"{p}.mlp.dense_h_to_4h.weight"), bias=self._p(f"{p}.mlp.dense_h_to_4h.bias"), gelu=True, aux_out=h1)
         y = K.gemm(g, self._w(f"{p}.mlp.dense_4h_to_h.weight"), bias=self._p(f"{p}.mlp.dense_4h_to_h.bias"), residual=att)
         saved = (x, mean, rstd, a1, a2, qkv, o, lse, h1, g) if keep else None
@@ -312,15 +343,18 @@ class B200GPTNeoXForCausalLM(_FlatModule):
     # ------------------------------------------------------------------ whole-model forward / backward
     def _forward_hidden(self, ids: torch.Tensor, keep: bool):
         B, S = ids.shape
+        self._wait_bucket(self.flat.range_of(["gpt_neox.embed_in.weight"]))
         x = K.embedding_fwd(ids.reshape(-1), self._w("gpt_neox.embed_in.weight"))
         saved_layers = []
         for i in range(self.L):
+            self._wait_bucket(self._layer_ranges[i])
             if keep and self.gradient_checkpointing:
                 saved_layers.append(x)  # recompute the layer in backward
                 x, _ = self._layer_fwd(i, x, B, S, keep=False)
             else:
                 x, sv = self._layer_fwd(i, x, B, S, keep=keep)
                 saved_layers.append(sv)
+        self._wait_bucket(self._head_range())
         xf, _, mean, rstd = K.layernorm_fwd(x, self._p("gpt_neox.final_layer_norm.weight"), self._p("gpt_neox.final_layer_norm.bias"), self.eps)
         return x, xf, mean, rstd, saved_layers
 
@@ -329,7 +363,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         B, S = ids.shape
         x_last, xf, mean, rstd, saved_layers = self._forward_hidden(ids, keep=True)
         logits = K.gemm(xf, self._w("embed_out.weight"))  # [T, V] bf16 — overwritten in place by dlogits
-        loss, _ = K.cross_entropy_(logits, targets.reshape(-1), V=self.V, write_grad=True)
+        loss, _ = K.cross_entropy_(logits, targets.reshape(-1), V=self.V, write_grad=True, grad_scale=self.loss_scale)
         ctx = SimpleNamespace(ids=ids, B=B, S=S, saved_layers=saved_layers, x_last=x_last, xf=xf, mean=mean, rstd=rstd, dlogits=logits)
         return loss, ctx
 

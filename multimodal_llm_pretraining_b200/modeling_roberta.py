@@ -141,6 +141,8 @@ class B200RobertaForMaskedLM(_FlatModule):
         head.decoder = _TiedDecoder(emb.word_embeddings.weight, head.bias)
         self.lm_head = head
         self.grad_ready_hook = None
+        self.param_wait_hook = None
+        self._fwd_buckets = list(reversed(self.comm_buckets()))  # embeddings, layers 0..L-1, head
         self.gradient_checkpointing = False
         self._step_seed = 0  # bumped once per training forward: every micro-batch draws fresh masks
         self._cur_seed = 0   # the seed base of the forward/backward currently running
@@ -219,7 +221,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         return self.flat.view(self.flat.master, name)
 
     def _g(self, name):
-        return self.flat.view(self.flat.grad, name)
+        return self.flat.gview(name)
 
     def _qkv_w(self, p):  # [3h, h] bf16: query | key | value rows
         return self.flat.view_span(self.flat.shadow, f"{p}.attention.self.query.weight", (3 * self.h, self.h))
@@ -228,7 +230,10 @@ class B200RobertaForMaskedLM(_FlatModule):
         return self.flat.view_span(buf, f"{p}.attention.self.query.bias", (3 * self.h,))
 
     def _qkv_gw(self, p):
-        return self.flat.view_span(self.flat.grad, f"{p}.attention.self.query.weight", (3 * self.h, self.h))
+        return self.flat.gview_span(f"{p}.attention.self.query.weight", (3 * self.h, self.h))
+
+    def _qkv_gb(self, p):
+        return self.flat.gview_span(f"{p}.attention.self.query.bias", (3 * self.h,))
 
     def _drop(self, x, residual, site: int):
         """dropout(x) + residual with the mask of (step seed, site); identity add when p == 0 is done by the GEMM epilogue."""
@@ -262,7 +267,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         else:
             s1 = K.gemm(o2, wo, bias=bo, residual=x)
         x1, _, mean1, rstd1 = K.layernorm_fwd(s1, self._p(f"{p}.attention.output.LayerNorm.weight"), self._p(f"{p}.attention.output.LayerNorm.bias"), self.eps)
-        h1 = torch.empty(B * S, self.inter, dtype=BF16, device=x.device)
+        h1 = torch.empty(B * S, self.inter, dtype=x.dtype, device=x.device)
         g = K.gemm(x1, self._w(f"{p}.intermediate.dense.weight"), bias=self._p(f"{p}.intermediate.dense.bias"), gelu=True, aux_out=h1)
         w2, b2 = self._w(f"{p}.output.dense.weight"), self._p(f"{p}.output.dense.bias")
         if drop:
@@ -301,13 +306,14 @@ class B200RobertaForMaskedLM(_FlatModule):
                         d4[:, :, 0], d4[:, :, 1], d4[:, :, 2], causal=False, scale=hd ** -0.5,
                         dropout_p=self.p_attn if train else 0.0, dropout_seed=self._seed(4 * i + 3))
         K.gemm(dqkv, x, a_mn=True, b_mn=True, out=self._qkv_gw(p), accumulate=True)
-        K.colsum_(dqkv, self._qkv_b(p, self.flat.grad))
+        K.colsum_(dqkv, self._qkv_gb(p))
         return K.gemm(dqkv, self._qkv_w(p), b_mn=True, residual=ds1)  # + residual branch of s1
 
     # ------------------------------------------------------------------ whole model
     def _embed(self, ids: torch.Tensor, train: bool):
         e = "roberta.embeddings"
         B, S = ids.shape
+        self._wait_bucket(self._fwd_buckets[0])  # embeddings (+ the tied decoder matrix the head reads)
         pos = K.roberta_position_ids(ids, self.pad_id)
         tok = torch.zeros_like(ids)  # token_type_ids default to 0 (HF:modeling_roberta.py:106-116)
         emb = K.embedding3_fwd(ids.reshape(-1), self._w(f"{e}.word_embeddings.weight"), pos.reshape(-1), self._w(f"{e}.position_embeddings.weight"),
@@ -318,6 +324,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         return x0, (pos, emb, mean, rstd)
 
     def _head_logits(self, x: torch.Tensor, keep: bool):
+        self._wait_bucket(self._fwd_buckets[-1])
         d_pre = torch.empty_like(x) if keep else None
         d = K.gemm(x, self._w("lm_head.dense.weight"), bias=self._p("lm_head.dense.bias"), gelu=True, aux_out=d_pre)
         n, _, mean, rstd = K.layernorm_fwd(d, self._p("lm_head.layer_norm.weight"), self._p("lm_head.layer_norm.bias"), self.eps)
@@ -331,6 +338,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         x, emb_saved = self._embed(ids, True)
         saved_layers = []
         for i in range(self.L):
+            self._wait_bucket(self._fwd_buckets[1 + i])
             if self.gradient_checkpointing:
                 saved_layers.append(x)  # recompute the layer in backward
                 x, _ = self._layer_fwd(i, x, B, S, True)
@@ -338,7 +346,7 @@ class B200RobertaForMaskedLM(_FlatModule):
                 x, sv = self._layer_fwd(i, x, B, S, True)
                 saved_layers.append(sv)
         logits, head_saved = self._head_logits(x, keep=True)
-        loss, _ = K.cross_entropy_(logits, labels.reshape(-1), V=self.V, write_grad=True)
+        loss, _ = K.cross_entropy_(logits, labels.reshape(-1), V=self.V, write_grad=True, grad_scale=self.loss_scale)
         ctx = SimpleNamespace(ids=ids, B=B, S=S, emb=emb_saved, layers=saved_layers, head=head_saved, dlogits=logits, seed=self._cur_seed)
         return loss, ctx
 
@@ -350,12 +358,12 @@ class B200RobertaForMaskedLM(_FlatModule):
         hook = self.grad_ready_hook
         x, d_pre, d, n, mean, rstd = ctx.head
         dl = ctx.dlogits
-        g_dec = f.view_alloc(f.grad, "roberta.embeddings.word_embeddings.weight")
+        g_dec = f.gview_alloc("roberta.embeddings.word_embeddings.weight")
         K.gemm(dl, n, a_mn=True, b_mn=True, out=g_dec, accumulate=True, alpha=alpha)
         # decoder bias grad = alpha * colsum(dlogits)
         bsum = torch.zeros(self.Vp, dtype=torch.float32, device=dl.device)
         K.colsum_(dl, bsum)
-        f.view_alloc(f.grad, "lm_head.bias").add_(bsum * alpha)
+        f.gview_alloc("lm_head.bias").add_(bsum * alpha)
         dn = K.gemm(dl, f.view_alloc(f.shadow, "roberta.embeddings.word_embeddings.weight"), b_mn=True, alpha=alpha)
         ctx.dlogits = None
         dd = K.layernorm_bwd(d, mean, rstd, self._p("lm_head.layer_norm.weight"), dn,
@@ -412,6 +420,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         with torch.no_grad():
             x, _ = self._embed(ids, False)
             for i in range(self.L):
+                self._wait_bucket(self._fwd_buckets[1 + i])
                 x, _ = self._layer_fwd(i, x, B, S, False)
             logits, _ = self._head_logits(x, keep=False)
             out_logits = logits[:, : self.V].reshape(B, S, self.V) if logits.numel() <= (1 << 28) else None

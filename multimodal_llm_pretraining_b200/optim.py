@@ -93,10 +93,20 @@ class B200Adam(torch.optim.Optimizer):
         return [tuple(r) for r in self._shard]
 
     def set_shard(self, ranges) -> None:
-        """ZeRO-1: restrict the update (and the moment buffers) to the flat-buffer element ranges this rank owns."""
+        """ZeRO-1/2: restrict the update (and the moment buffers) to the flat-buffer element ranges this rank owns. Must be
+        called before any state exists: re-sharding live moments would silently drop them."""
+        ranges = [tuple(r) for r in ranges]
+        if self._m is not None and self._step > 0 and ranges != self._ranges():
+            raise RuntimeError("B200Adam.set_shard: optimizer state already exists for a different shard; build the TrainEngine "
+                               "before loading optimizer state (TrainEngine.load_checkpoint does)")
         self._shard = ranges
         self._built_for = None
         self._m = self._v = None
+
+    def chunk_table(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """(chunk_start int64, chunk_len int32) device arrays covering exactly the parameter elements this rank updates."""
+        self._ensure_built()
+        return self._chunk_start, self._chunk_len
 
     def _ensure_built(self) -> None:
         f = self._flat
@@ -105,7 +115,11 @@ class B200Adam(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ torch.optim API
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: torch.Tensor | None = None):
+    def step(self, closure=None, grad_scale: torch.Tensor | None = None, skip_flag: torch.Tensor | None = None,
+             grads: torch.Tensor | None = None, grads_packed: bool = False):
+        """grad_scale: device fp32 scalar multiplied into every gradient (clip coefficient, fp16 unscale); skip_flag: device
+        int32, non-zero = leave parameters and moments untouched (fp16 overflow); grads / grads_packed: a packed shard
+        gradient buffer laid out like the moments (ZeRO-2) instead of the flat gradient buffer."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -125,9 +139,9 @@ class B200Adam(torch.optim.Optimizer):
             grad_scale = f.pending_grad_scale
         f.pending_grad_scale = None
         f.sync_shadow()  # no-op unless the master was edited through torch since the last step
-        K.adam_step(f.master, f.grad, self._m, self._v, f.shadow, self._state_base, self._chunk_start, self._chunk_len,
-                    self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step,
-                    chunk_state=self._chunk_state)
+        K.adam_step(f.master, f.grad if grads is None else grads, self._m, self._v, f.shadow, self._state_base, self._chunk_start,
+                    self._chunk_len, self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step,
+                    chunk_state=self._chunk_state, skip_flag=skip_flag, g_packed=grads_packed)
         return loss
 
     def zero_grad(self, set_to_none: bool = False) -> None:

@@ -205,7 +205,7 @@ def _toy_classes():
             names = list(ctx.leaves)
             grads = torch.autograd.grad(ctx.loss, [ctx.leaves[n] for n in names], grad_out)
             for n, g in zip(names, grads):
-                f.view(f.grad, n).add_(g)
+                f.gview(n).add_(g)  # the flat gradient buffer, or the engine's transient bucket buffer under ZeRO-2
             if model.grad_ready_hook:
                 for b in model.comm_buckets():  # backward order: head first, embedding last
                     model.grad_ready_hook(*b)
@@ -245,7 +245,7 @@ def _toy_classes():
             n = sum(hi - lo for lo, hi in self.ranges)
             self._m, self._v = torch.zeros(n), torch.zeros(n)
 
-        def step(self):
+        def step(self, grads=None, grads_packed=False):
             f = self.flat
             self.t += 1
             scale = 1.0 if f.pending_grad_scale is None else float(f.pending_grad_scale)
@@ -253,7 +253,8 @@ def _toy_classes():
             off = 0
             for lo, hi in self.ranges:
                 n = hi - lo
-                _adam_ref(f.master[lo:hi], f.grad[lo:hi] * scale, self._m[off:off + n], self._v[off:off + n], self.t, lr=self.lr)
+                g = grads[off:off + n] if grads_packed else f.grad[lo:hi]  # ZeRO-2: packed shard accumulator, laid out like m / v
+                _adam_ref(f.master[lo:hi], g * scale, self._m[off:off + n], self._v[off:off + n], self.t, lr=self.lr)
                 f.shadow[lo:hi] = f.master[lo:hi].to(torch.bfloat16)
                 off += n
 
@@ -276,7 +277,7 @@ def _engine_worker(rank, world, port, q, tmpdir):
         from multimodal_llm_pretraining_b200.engine import TrainEngine
 
         K.sumsq_ = lambda x, out: out.add_((x.double() ** 2).sum().float())
-        K.clip_coef = lambda sumsq, max_norm: (sumsq.sqrt(), torch.clamp(max_norm / (sumsq.sqrt() + 1e-6), max=1.0))
+        K.clip_coef = lambda sumsq, max_norm, **kw: (sumsq.sqrt(), torch.clamp(max_norm / (sumsq.sqrt() + 1e-6), max=1.0))
         Toy, ToyAdam = _toy_classes()
         g = torch.Generator().manual_seed(100)
         xs = torch.randint(0, 32, (3, 2, world, 16), generator=g)       # [step, micro, rank, tokens]
@@ -308,6 +309,20 @@ def _engine_worker(rank, world, port, q, tmpdir):
             finals[strategy] = {"master": f.master.clone(), "shadow": f.shadow.clone()}
         moved = (finals["ddp"]["master"] - Toy().flat.master).abs().max()
         assert moved > 1e-3, "the toy problem must actually train"
+
+        # ZeRO-2: no full gradient buffer; every micro-batch's bucket is reduce-scattered and accumulated into the shard
+        model = Toy()
+        eng = TrainEngine(model, ToyAdam(model.flat), None, max_grad_norm=0.05, gradient_accumulation_steps=2, strategy="zero2")
+        assert model.flat.grad is None and all(p.grad is None for p in model.parameters())
+        assert eng._gshard.numel() == sum(hi - lo for lo, hi in eng.plan.owned_ranges()) < model.flat.numel
+        assert eng.zero2_transient_bytes() == 4 * sum(e - s for s, e in eng.plan.buckets)  # three distinct bucket sizes here: one buffer each
+        run(eng, range(3))
+        assert float(eng._gshard.abs().max()) == 0.0 and not eng._active
+        model.state_dict()
+        # same mean gradient, summed in a different order (per micro-batch across ranks, then over micro-batches)
+        ref = finals["ddp"]["master"]
+        err = ((model.flat.master - ref).norm() / (ref - Toy().flat.master).norm()).item()
+        assert err < 1e-5, err
 
         # ZeRO-1 checkpoint: 2 steps, save, fresh engine (different init), load, third step == uninterrupted
         model = Toy()
