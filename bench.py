@@ -39,11 +39,19 @@ def parse():
     ap.add_argument("--mbs", type=int, default=None, help="micro-batch size (default 16 for Pythia, 64 for RoBERTa)")
     ap.add_argument("--grad-acc", type=int, default=16)
     ap.add_argument("--seq-len", type=int, default=None, help="RoBERTa only: 512 (default) or 128")
-    ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1"])
+    ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1", "zero2"])
     ap.add_argument("--checkpointing", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
+                    help="bf16 (every BASELINE.json config) or fp16 + dynamic loss scaling (the reference's own precision for Pythia != 1b / RoBERTa)")
+    ap.add_argument("--batch-preserving", action="store_true",
+                    help="grad-acc = 1024 / (gpus * mbs): the reference's rule W * mbs * ga = batch_size (src/models/__init__.py:99-102)")
+    ap.add_argument("--phases", action="store_true",
+                    help="after the timed region, one more instrumented step: per-rank micro-batch and optimizer-phase device times in the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tokens", type=int, default=1024,
                     help="predicted tokens of the bounded CPU sample (one sequence): ~10 s per step on 16 cores, two steps")
+    ap.add_argument("--no-config1", action="store_true", help="skip the BASELINE.json configs[0] CPU figures (Pythia-160m, OMP=1 and all cores)")
+    ap.add_argument("--config1-tokens", default="256,2048", help="predicted tokens of the bounded config-1 samples: OMP=1, all cores")
     return ap.parse_args()
 
 
@@ -143,12 +151,19 @@ def cpu_reference_step_factory(model_name: str, sample_tokens: int):
         return step, "port", "oracle/neox_oracle.py fp32"
 
 
-def run_cpu_baseline(model_name: str, sample_tokens: int, steps: int, warmup: int) -> dict:
-    # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would otherwise make the
-    # reference arm at N > 1 a single-threaded (16x slower) run
+def _all_cores() -> int:
     try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, RuntimeError):
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_baseline(model_name: str, sample_tokens: int, steps: int, warmup: int, threads: int | None = None) -> dict:
+    # default: all the host cores this process may use — torchrun exports OMP_NUM_THREADS=1 to every rank, which would otherwise
+    # make the reference arm at N > 1 a single-threaded (16x slower) run; threads=1 is the reference-faithful setting (.env:4)
+    try:
+        torch.set_num_threads(threads or _all_cores())
+    except RuntimeError:
         pass
     step, kind, what = cpu_reference_step_factory(model_name, sample_tokens)
     for _ in range(warmup):
@@ -163,6 +178,20 @@ def run_cpu_baseline(model_name: str, sample_tokens: int, steps: int, warmup: in
             "s_per_step": dt}
 
 
+def run_config1_cpu(tokens: str = "256,2048", steps: int = 2, warmup: int = 1) -> dict:
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: Pythia-160m causal-LM step, micro-batch 4 x 2049 tokens,
+    fp32 (SURVEY §8d "CPU baseline"), at the reference-faithful OMP_NUM_THREADS=1 (/root/reference/.env:4) and at all cores.
+    Bounded: a full 4 x 2049 micro-batch takes minutes on one core, so each setting times one sequence of the micro-batch,
+    truncated (the per-token cost of a causal LM GROWS with context, so the truncated sample flatters the CPU)."""
+    out = {"workload": "pythia-160m, micro-batch 4 x 2049 tokens, fp32, HF GPTNeoXForCausalLM + torch.optim.Adam + clip (BASELINE.json configs[0])"}
+    t1, tall = (int(x) for x in tokens.split(","))
+    for key, threads, toks in (("omp_num_threads_1", 1, t1), ("all_cores", None, tall)):
+        r = run_cpu_baseline("pythia-160m", toks, steps, warmup, threads=threads)
+        out[key] = {"tokens_per_s": r["value"], "cores": r["cores"], "s_per_step": r["s_per_step"],
+                    "sample": f"1 of the 4 sequences, {toks} predicted tokens, {steps} timed steps after {warmup} warm-up"}
+    return out
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,13 +199,14 @@ def main_reference(a):
     if a.mbs is None:
         a.mbs = 16
     cb = run_cpu_baseline(a.model, a.cpu_sample_tokens, a.steps, a.warmup)
+    config1 = None if a.no_config1 else run_config1_cpu(a.config1_tokens)
     line = {
         "impl": "reference", "metric": "train_tokens_per_s", "value": cb["value"], "unit": "tokens/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{a.model} pretraining step (fwd+bwd+Adam), mbs {a.mbs} x 2049 tokens, grad-acc {a.grad_acc}; "
                                f"CPU arm runs a bounded sample of it: {cb['sample']}"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {**{k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}, "config1": config1},
         "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,14 +243,19 @@ def main_b200(a):
     cfg = mc.config_dict()
     is_roberta = a.model == "roberta"
     if a.mbs is None:
-        a.mbs = 64 if is_roberta else 16
+        a.mbs = (256 if a.seq_len == 128 else 64) if is_roberta else 16  # 32 768 tokens per micro-batch either way
+    if a.batch_preserving:
+        a.grad_acc = max(1, mc.batch_size // (world * a.mbs))
     if is_roberta:
         S_in = S_pred = a.seq_len or mc.sequence_length  # masked LM: every position is predicted (labels = input_ids)
     else:
         S_in = mc.sequence_length  # 2049 tokens in, 2048 predicted
         S_pred = S_in - 1
     torch.manual_seed(0)
-    model = mc.build_model(use_custom_kernels=True).to(dev).train()
+    model = mc.build_model(use_custom_kernels=True)
+    if a.precision == "fp16":
+        model.set_compute_dtype(torch.float16)
+    model = model.to(dev).train()
     if a.checkpointing:
         model.gradient_checkpointing_enable()
     okw = dict(mc.optimizer_kwargs)
@@ -310,30 +345,45 @@ def main_b200(a):
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     per_gpu = value / world
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    # DRAM traffic of the GEMM variants from the committed `ncu --set full` capture (per launch, MB read + written)
-    ncu_traffic = {}
-    try:
-        names = ["fwd+bias qkv", "fwd+bias+gelu+aux mlp_up", "fwd+bias+residual mlp_down", "dgrad*dgelu", "dgrad+residual", "wgrad split-K"]
-        rows = [ln.split() for ln in (ROOT / "profiles" / "r01_ncu_all_kernels.txt").read_text().splitlines() if ln.startswith("gemm_kernel<")]
-        for nm, r in zip(names, rows):  # columns after the kernel name: time us, dram rd MB, dram wr MB, ...
-            k = next(i for i, tok in enumerate(r) if tok.endswith(">")) + 1
-            ncu_traffic[nm] = {"time_us": float(r[k]), "dram_mb": float(r[k + 1]) + float(r[k + 2])}
-    except Exception:
-        ncu_traffic = None
+    # opt-in: per-rank device times of one more instrumented step (micro-batches, boundary micro-batch, optimizer phases)
+    phases = None
+    if a.phases:
+        eng.profile_phases = True
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(ga + 2)]
+        evs[0].record()
+        for m in range(ga):
+            eng.manual_training_step({"input_ids": resident[m % n_host], "labels": resident[m % n_host]})
+            evs[m + 1].record()
+        eng.manual_optimization_step()
+        evs[ga + 1].record()
+        torch.cuda.synchronize()
+        eng.profile_phases = False
+        micro = [evs[i].elapsed_time(evs[i + 1]) for i in range(ga)]
+        mine = {"rank": rank, "micro_ms_plain_mean": sum(micro[:-1]) / max(1, ga - 1) if ga > 1 else micro[0], "micro_ms_boundary": micro[-1],
+                "micro_ms_min": min(micro), "micro_ms_max": max(micro), "optim_ms": evs[ga].elapsed_time(evs[ga + 1]),
+                "optim_phases_ms": eng.last_phase_ms, "step_ms": evs[0].elapsed_time(evs[ga + 1])}
+        if world > 1:
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+        else:
+            allp = [mine]
+        phases = {"per_rank": allp, "slowest_rank_step_ms": max(p_["step_ms"] for p_ in allp), "fastest_rank_step_ms": min(p_["step_ms"] for p_ in allp),
+                  "note": "device times (CUDA events) of one step after the timed region; the step time of the job is the slowest rank's"}
 
     if rank == 0:
         cpu = None
         if not a.no_cpu_baseline and world == 1 and not is_roberta:  # the CPU arm is the Pythia reference path
             cpu = run_cpu_baseline(a.model, a.cpu_sample_tokens, 2, 1)  # ~12 s of CPU work in total
+            cpu["config1"] = None if a.no_config1 else run_config1_cpu(a.config1_tokens)  # + ~35 s: Pythia-160m at OMP=1 and at all cores
         line = {
             "metric": "train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
             "config": {
                 "workload": f"{a.model} pretraining step: {ga} micro-batches x ({mbs} x {S_in} tokens, {S_pred} predicted) fwd+bwd "
                             f"+ clip + fused Adam (random-init weights, uniform random tokens)",
                 "model": a.model, "micro_batch": mbs, "grad_acc": ga, "global_batch_sequences": world * ga * mbs,
-                "seq_len": S_in, "parallelism": f"{strategy}x{world}", "activation_checkpointing": bool(a.checkpointing),
+                "seq_len": S_in, "parallelism": f"{strategy}x{world}", "activation_checkpointing": bool(a.checkpointing), "precision": a.precision,
                 **({"note": "hidden dropout 0.1 and attention-probability dropout 0.1 applied (roberta-large config)"} if is_roberta else {}),
                 "l2": "working set per step (>= 2 GB of weights, > 30 GB of activations) far exceeds the 126 MB L2; no explicit flush",
             },
@@ -349,16 +399,19 @@ def main_b200(a):
             "training_days": mc.training_steps * (mc.batch_size / (world * ga * mbs)) * (ms_per_step / 1e3) / 86400.0,
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
-                "frac": (achieved / peak_sust) if achieved else None, "traffic": None,
-                "ncu_dram_per_launch": ncu_traffic,  # per GEMM variant at the step's shapes (profiles/r01_ncu_all_kernels.txt); the
-                # aggregate above spans all variants, so there is no single per-launch `traffic` figure for it
+                "frac": (achieved / peak_sust) if achieved else None,
+                # the aggregate spans every GEMM variant of the step, so there is no single per-launch DRAM figure for it; the
+                # per-variant dram__bytes of this build are in profiles/ (ncu --set full), not re-stated here from a file
+                "traffic": None,
                 "kernel": "gemm_kernel (tcgen05 bf16 GEMM, all fwd/dgrad/wgrad launches of one step)",
                 "how": f"sum of 2*M*N*K over {len(prof)} launches / sum of their CUDA-event durations in a separate instrumented step; "
                        f"GEMM share of step {gemm_ms / step_ms_plain:.3f}; peak = {peak_src}",
             },
         }
+        if phases is not None:
+            line["phases"] = phases
         if cpu is not None:
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "config1")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

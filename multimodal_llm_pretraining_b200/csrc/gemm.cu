@@ -55,11 +55,19 @@ struct GemmParams {
     float alpha_host;
     int split_k;  // fp32-accumulate outputs only: the reduction is cut into split_k ranges, each red.add'ed into C
     int debug;  // B200_GEMM_DEBUG (perf triage only): bit0 = skip epilogue math+stores, bit1 = skip TMEM loads as well
+    // tile raster: group_m = 0 -> n runs fastest (a wave of CTAs = a few whole A row panels x every B panel: A is fetched from
+    // DRAM once); group_m = g > 0 -> groups of g m-tiles, m fastest inside a group (the g A panels stay L2-resident while B streams)
+    int group_m;
+    unsigned long long hint_a, hint_b;  // L2 eviction-priority hints of the operand loads (common.cuh)
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-    // groups of 8 m-tiles; inside a group m runs fastest so 8 consecutive CTAs share one B (weight) tile
-    constexpr int GROUP = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int GROUP, int& tm, int& tn) {
+    if (GROUP <= 0) {  // n fastest
+        tm = tile / tiles_n;
+        tn = tile - tm * tiles_n;
+        return;
+    }
+    // groups of GROUP m-tiles; inside a group m runs fastest so GROUP consecutive CTAs share one B tile
     const int group_size = GROUP * tiles_n;
     const int group = tile / group_size;
     const int first_m = group * GROUP;
@@ -265,7 +273,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ks = unit / per_split;
         const int tile = unit - ks * per_split;
         z = tile / tiles_per_z;
-        tile_coords(tile - z * tiles_per_z, p.tiles_m, p.tiles_n, tm, tn);
+        tile_coords(tile - z * tiles_per_z, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
         kb0 = p.causal_k ? (tm * TILE_M) / GEMM_BK : 0;
         kb1 = num_kb;
         if (p.split_k > 1) {
@@ -292,21 +300,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (rank == 0) mbar_expect_tx(&full[s], CG * (A_BYTES + B_BYTES));
                     uint8_t* a_dst = sA + s * A_BYTES;
                     uint8_t* b_dst = sB + s * B_BYTES;
-                    auto ld = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-                        if (CG == 2) tma_load_2d_pair(dst, m, &full[s], c0, c1);
-                        else tma_load_2d(dst, m, &full[s], c0, c1);
+                    auto ld = [&](void* dst, const CUtensorMap* m, int c0, int c1, uint64_t hint) {
+                        if (CG == 2) tma_load_2d_pair_hint(dst, m, &full[s], c0, c1, hint);
+                        else tma_load_2d_hint(dst, m, &full[s], c0, c1, hint);
                     };
                     if (!A_MN) {
-                        ld(a_dst, &tmA, ak0 + kb * GEMM_BK, m0);
+                        ld(a_dst, &tmA, ak0 + kb * GEMM_BK, m0, p.hint_a);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < GEMM_BM / 64; ++j) ld(a_dst + j * SLICE_BYTES, &tmA, m0 + j * 64, ak0 + kb * GEMM_BK);
+                        for (int j = 0; j < GEMM_BM / 64; ++j) ld(a_dst + j * SLICE_BYTES, &tmA, m0 + j * 64, ak0 + kb * GEMM_BK, p.hint_a);
                     }
                     if (!B_MN) {
-                        ld(b_dst, &tmB, bk0 + kb * GEMM_BK, n0);
+                        ld(b_dst, &tmB, bk0 + kb * GEMM_BK, n0, p.hint_b);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BNH / 64; ++j) ld(b_dst + j * SLICE_BYTES, &tmB, n0 + j * 64, bk0 + kb * GEMM_BK);
+                        for (int j = 0; j < BNH / 64; ++j) ld(b_dst + j * SLICE_BYTES, &tmB, n0 + j * 64, bk0 + kb * GEMM_BK, p.hint_b);
                     }
                     if (++s == STAGES) s = 0, ph ^= 1;
                 }
@@ -661,6 +669,37 @@ static void fill_params(const b200_gemm_args* a, GemmParams& p) {
     p.Z = 1, p.zH = 1;
     p.alpha_host = 1.0f;
     p.split_k = 1;
+    p.group_m = 8;
+    p.hint_a = L2_EVICT_NORMAL, p.hint_b = L2_EVICT_NORMAL;
+}
+
+// Raster and L2 policy of a plain (non-batched) problem. A wave = one tile per CTA (pair), all streaming K in lockstep, so what
+// costs DRAM bytes is (a) operand panels that are touched by more than one wave and have left L2 in between, (b) panels shared by
+// tiles of different waves because a wave boundary cuts through their group. Round 1 walked groups of 8 m-tiles with m fastest:
+// on 74 CTA pairs every group straddles two waves along n, so every A panel was fetched twice and the weights once per wave
+// (ncu: 1.96x-2.24x the algorithmic bytes on the K = 8192 shapes). Now: when A (activations / output gradients) is the larger
+// operand and the whole B fits in a fraction of L2, n runs fastest — a wave is a few complete A panels times every B panel, A is
+// fetched once and marked EVICT_FIRST, B is marked EVICT_LAST and stays resident across waves. Otherwise (LM head: 206 MB of
+// weights) groups of m-tiles whose A panels fit in L2 stay resident while B streams. B200_GEMM_GROUP_M / B200_GEMM_HINTS override
+// (perf triage only).
+static void choose_raster(const b200_gemm_args* a, GemmParams& p, int tile_m) {
+    static const int env_group = getenv("B200_GEMM_GROUP_M") ? atoi(getenv("B200_GEMM_GROUP_M")) : -1;
+    static const int env_hints = getenv("B200_GEMM_HINTS") ? atoi(getenv("B200_GEMM_HINTS")) : 1;
+    const double a_bytes = 2.0 * a->M * a->K, b_bytes = 2.0 * a->N * a->K;
+    const double panel_a = 2.0 * tile_m * a->K / (p.split_k > 0 ? p.split_k : 1);
+    constexpr double L2_RESIDENT = 40e6;  // what can be expected to stay in the 126 MB L2 next to a streaming operand
+    const int tiles_m = (a->M + tile_m - 1) / tile_m;
+    if (b_bytes <= L2_RESIDENT || a_bytes >= b_bytes) {
+        p.group_m = 0;
+        if (env_hints && b_bytes <= L2_RESIDENT) p.hint_a = L2_EVICT_FIRST, p.hint_b = L2_EVICT_LAST;
+    } else {
+        int g = static_cast<int>(L2_RESIDENT / panel_a);
+        if (g < 8) g = 8;
+        if (g > tiles_m) g = tiles_m;
+        p.group_m = g;
+        if (env_hints && g * panel_a <= L2_RESIDENT) p.hint_a = L2_EVICT_LAST, p.hint_b = L2_EVICT_FIRST;
+    }
+    if (env_group >= 0) p.group_m = env_group;
 }
 
 // dOut[z] = alpha * A[z]^T-or-not x B[z] over Z = nb * nh problems sharing the tensor maps (see GemmParams); bf16 TMA-stored
@@ -720,8 +759,10 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
             }
             p.split_k = best;
         }
+        choose_raster(a, p, 256);
         return dispatch_major<256, 5, 2>(a, p, st);
     }
+    choose_raster(a, p, 128);
     if (a->N > 128) return dispatch_major<256, 4, 1>(a, p, st);
     return dispatch_major<128, 6, 1>(a, p, st);
 }

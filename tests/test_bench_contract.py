@@ -12,11 +12,15 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_reference_arm_json_line():
     res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--model", "pythia-70m", "--steps", "1", "--warmup", "1",
-                          "--cpu-sample-tokens", "32"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--cpu-sample-tokens", "32", "--config1-tokens", "8,16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-1500:]
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1, res.stdout
     d = json.loads(lines[0])
+    # BASELINE.json configs[0] (Pythia-160m fp32 on the host) at the reference-faithful OMP_NUM_THREADS=1 and at all cores
+    c1 = d["cpu_baseline"]["config1"]
+    assert "pythia-160m" in c1["workload"] and c1["omp_num_threads_1"]["cores"] == 1 and c1["omp_num_threads_1"]["tokens_per_s"] > 0
+    assert c1["all_cores"]["cores"] >= 1 and c1["all_cores"]["tokens_per_s"] > 0
     assert d["impl"] == "reference" and d["metric"] == "train_tokens_per_s" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
@@ -31,7 +35,7 @@ def test_reference_arm_uses_all_cores_under_torchrun():
 
     env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
     res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--model", "pythia-70m", "--steps", "1",
-                          "--warmup", "0", "--cpu-sample-tokens", "16"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+                          "--warmup", "0", "--cpu-sample-tokens", "16", "--no-config1"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stderr[-1500:]
     d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][0])
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
