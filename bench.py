@@ -222,7 +222,7 @@ def main_b200(a):
     from multimodal_llm_pretraining_b200.engine import TrainEngine
     from multimodal_llm_pretraining_b200.models import get_model_class
     from multimodal_llm_pretraining_b200.models.configs import neox_train_flops_per_sequence, roberta_train_flops_per_sequence
-    from multimodal_llm_pretraining_b200.optim import get_scheduler
+    from multimodal_llm_pretraining_b200.optim import fused_optimizer_class, get_scheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -260,7 +260,7 @@ def main_b200(a):
         model.gradient_checkpointing_enable()
     okw = dict(mc.optimizer_kwargs)
     okw["weight_decay"] = 0.0  # HF Trainer's param groups override the kwarg with TrainingArguments.weight_decay = 0
-    opt = mc.optimizer(model.parameters(), **okw)
+    opt = fused_optimizer_class(mc.optimizer)(model.parameters(), **okw)
     skw = dict(mc.scheduler_kwargs)
     warm = skw.pop("num_warmup_steps", 0)
     sched = get_scheduler(mc.scheduler_type, opt, warm, mc.training_steps, skw)

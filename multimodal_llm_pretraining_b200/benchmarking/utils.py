@@ -14,13 +14,28 @@ import torch
 import torch.distributed as dist
 
 from ..engine import TrainEngine
-from ..optim import get_scheduler
+from ..optim import fused_optimizer_class, get_scheduler
 from .data import ShardedBatchIterator
+
+
+def strategy_for(world_size: int, zero_stage: str = "0", fsdp_sharding: str = "no_shard") -> str:
+    """Sharding selection of the reference (src/train.py:126-181) -> engine strategy. DeepSpeed stage 2 and FSDP
+    shard_grad_op are the same algorithm here (optimizer state + gradients sharded, parameters replicated)."""
+    if world_size == 1:
+        return "none"
+    if zero_stage == "1":
+        return "zero1"
+    if zero_stage == "2" or fsdp_sharding == "shard_grad_op":
+        return "zero2"
+    if zero_stage == "0" and fsdp_sharding == "no_shard":
+        return "ddp"
+    raise NotImplementedError(f"zero_stage={zero_stage!r} fsdp_sharding={fsdp_sharding!r}: parameter sharding (ZeRO-3 / FSDP full_shard) "
+                              "and offload are outside this build's scope (SURVEY.md §2.3, §8f rank 3)")
 
 
 class ManualTrainer:
     def __init__(self, model, args: dict[str, Any], train_dataset, optimizer_cls_and_kwargs, scheduler_type="linear",
-                 zero_stage: str = "0", device: torch.device | None = None, seed: int = 0):
+                 zero_stage: str = "0", fsdp_sharding: str = "no_shard", device: torch.device | None = None, seed: int = 0):
         self.args = SimpleNamespace(**args)
         self.args.train_batch_size = self.args.per_device_train_batch_size
         self.train_dataset = train_dataset
@@ -29,6 +44,14 @@ class ManualTrainer:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
+        if not hasattr(model, "flat"):
+            raise NotImplementedError(
+                "ManualTrainer drives B200 modules (build_model(use_custom_kernels=True)); the naive HF module of "
+                "build_model(use_custom_kernels=False) is the parity oracle and the CPU baseline of bench.py --impl reference, "
+                "it has no GPU training path in this build (no accelerate / HF Trainer in the image)")
+        # precision of the reference's TrainingArguments (src/train.py:113-114): fp16 -> IEEE-half kernels + dynamic loss scaling
+        if args.get("fp16"):
+            model.set_compute_dtype(torch.float16)
         self.model = model.to(device).train()
         self.model_wrapped = self.model
         if self.args.gradient_checkpointing:
@@ -40,10 +63,11 @@ class ManualTrainer:
         decay = [p for n, p in self.model.named_parameters() if p.dim() >= 2]
         no_decay = [p for n, p in self.model.named_parameters() if p.dim() < 2]
         kw = {k: v for k, v in opt_kwargs.items() if k != "weight_decay"}
+        opt_cls = fused_optimizer_class(opt_cls)  # torch.optim.Adam / AdamW -> the fused B200 classes (same signature and rule)
         self.optimizer = opt_cls([{"params": decay, "weight_decay": wd}, {"params": no_decay, "weight_decay": 0.0}], **kw)
         self.lr_scheduler = get_scheduler(self.args.lr_scheduler_type, self.optimizer, self.args.warmup_steps,
                                           self.args.max_steps, self.args.lr_scheduler_kwargs)
-        strategy = "none" if self.world_size == 1 else ("zero1" if zero_stage == "1" else "ddp")
+        strategy = strategy_for(self.world_size, zero_stage, fsdp_sharding)
         self.engine = TrainEngine(self.model, self.optimizer, self.lr_scheduler, max_grad_norm=self.args.max_grad_norm,
                                   gradient_accumulation_steps=self.args.gradient_accumulation_steps, strategy=strategy)
         self.seed = seed
@@ -54,7 +78,7 @@ class ManualTrainer:
         return self.engine.manual_training_step(inputs)
 
     def manual_optimization_step(self, model):
-        self.engine.manual_optimization_step()
+        return self.engine.manual_optimization_step()
 
     def get_train_dataloader(self):
         return ShardedBatchIterator(self.train_dataset, self.args.per_device_train_batch_size, self.world_size, self.rank,

@@ -48,11 +48,9 @@ class PythiaModelClass(LanguageModelClass[PythiaT]):
 
     @property
     def optimizer(self) -> type[torch.optim.Optimizer]:
-        """src/models/pythia.py:43-45 returns torch.optim.Adam (L2-coupled). The B200 build hands out the fused
-        equivalent with identical constructor signature and update rule."""
-        from ..optim import B200Adam
-
-        return B200Adam
+        """src/models/pythia.py:43-45: torch.optim.Adam (L2-coupled). For a B200 module the trainer swaps it for the fused
+        equivalent (optim.fused_optimizer_class); the naive HF module keeps the torch class, as in the reference."""
+        return torch.optim.Adam
 
     @property
     def optimizer_kwargs(self) -> dict[str, Any]:  # :47-67

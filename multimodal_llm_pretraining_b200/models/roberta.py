@@ -39,10 +39,8 @@ class RobertaModelClass(LanguageModelClass[RobertaT]):
         return "fp16"
 
     @property
-    def optimizer(self) -> type[torch.optim.Optimizer]:
-        from ..optim import B200Adam
-
-        return B200Adam
+    def optimizer(self) -> type[torch.optim.Optimizer]:  # src/models/roberta.py:32-34; swapped for the fused class by the trainer
+        return torch.optim.Adam
 
     @property
     def optimizer_kwargs(self) -> dict[str, Any]:

@@ -174,6 +174,17 @@ class B200AdamW(B200Adam):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, **kw)
 
 
+def fused_optimizer_class(opt_cls: type[torch.optim.Optimizer]) -> type[torch.optim.Optimizer]:
+    """The model classes hand out the reference's own optimizer classes (torch.optim.Adam for Pythia, src/models/pythia.py:43-45;
+    torch.optim.AdamW for RoBERTa, src/models/roberta.py:32-34). For a B200 module the trainer swaps them for the fused
+    equivalents with the same constructor signature and update rule; anything else is used as is."""
+    if opt_cls is torch.optim.Adam:
+        return B200Adam
+    if opt_cls is torch.optim.AdamW:
+        return B200AdamW
+    return opt_cls
+
+
 # ---------------------------------------------------------------------------------------------------- LR schedules
 def cosine_with_min_lr_lambda(step: int, *, num_warmup_steps: int, num_training_steps: int, num_cycles: float = 0.5,
                               min_lr_rate: float = 0.0) -> float:

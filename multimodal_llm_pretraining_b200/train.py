@@ -3,8 +3,10 @@
 `_to_huggingface_args_dict()` reproduces the reference's HF TrainingArguments dict key for key (README.md:78-123 of the
 reference shows the expected output), including the FSDP option list and the DeepSpeed JSON for every ZeRO stage, so
 `scripts/to_training_arguments.py` keeps emitting the same artefact. `build_trainer()` returns the B200 step engine
-(multimodal_llm_pretraining_b200.benchmarking.utils.ManualTrainer) instead of transformers.Trainer; only
-zero_stage in {"0", "1"} with fsdp_sharding "no_shard" and no offload run on this build.
+(multimodal_llm_pretraining_b200.benchmarking.utils.ManualTrainer) instead of transformers.Trainer. What runs on this
+build: no sharding (DDP), zero_stage "1", zero_stage "2" / fsdp "shard_grad_op" (gradient sharding), bf16 or fp16 (+ dynamic
+loss scaling), with or without activation checkpointing; parameter sharding (ZeRO-3, FSDP full_shard / hybrid) and offload
+are out of scope.
 """
 from __future__ import annotations
 
@@ -72,7 +74,7 @@ class TrainingClass:
         )
 
     def runs_on_b200_engine(self) -> bool:
-        return (self.fsdp_sharding == "no_shard" and self.zero_stage in ("0", "1")
+        return (self.fsdp_sharding in ("no_shard", "shard_grad_op") and self.zero_stage in ("0", "1", "2")
                 and not self.zero_offload_optimizer and not self.zero_offload_params and not self.fsdp_offload)
 
     def build_trainer(self, model: nn.Module, train_dataset: Dataset, hf_training_args_overrides: dict[str, Any] = {},
@@ -88,10 +90,10 @@ class TrainingClass:
         if not self.runs_on_b200_engine():
             raise NotImplementedError(
                 f"sharding fsdp={self.fsdp_sharding!r} zero={self.zero_stage!r} offload is outside this build's scope "
-                "(DDP and ZeRO-1 only; SURVEY.md §2.3)")
+                "(DDP, ZeRO-1, ZeRO-2 / FSDP shard_grad_op; SURVEY.md §2.3)")
         args = self._to_huggingface_args_dict(**hf_training_args_overrides)
         return ManualTrainer(model=model, args=args, train_dataset=train_dataset, optimizer_cls_and_kwargs=(self.optimizer, dict(self.optimizer_kwargs)),
-                             scheduler_type=self.scheduler_type, zero_stage=self.zero_stage, **hf_trainer_kwargs_overrides)
+                             scheduler_type=self.scheduler_type, zero_stage=self.zero_stage, fsdp_sharding=self.fsdp_sharding, **hf_trainer_kwargs_overrides)
 
     def to_huggingface_args(self, **hf_training_args_overrides):
         from transformers import TrainingArguments  # needs accelerate; not available in every image

@@ -1,6 +1,6 @@
 """Mirrors scripts/benchmark.py of the reference (same arguments: --num-nodes --gpus-per-node --gpu-type --model --methods)
 on the B200 step engine: for every method combination of the reference's search space that is in this build's scope
-(no sharding -> DDP, zero_1, each with/without activation checkpointing) it runs the reference's three steps
+(no sharding -> DDP, zero_1, zero_2, fsdp_shard_grad_op, each with/without activation checkpointing) it runs the reference's three steps
 (experiments/training_time_empirical.py:43-138): find the largest power-of-two micro-batch -> benchmark the
 accumulate / optimize times (device-timed) -> training days = training_steps * step_time / 86400.
 
@@ -50,8 +50,13 @@ def search_space(methods: str):  # scripts/benchmark.py:45-64
     return list(product(free_lunch, ckpt, sharding, offloading))
 
 
+RESULTS_FILE = Path(__file__).resolve().parent.parent / "results" / "training_time_empirical.jsonl"
+PRECISION = "bf16"  # "bf16" (every BASELINE.json config) or "reference" (the model class's mixed_precision: fp16 for Pythia != 1b, RoBERTa)
+
+
 def build_benchmarking_trainer(config: TrainingConfig, num_samples: int = 4096):  # experiments/training_time_empirical.py:17-40
-    training_class = config.training_class(num_training_steps=1, micro_batch_size=1, gradient_accumulation_steps=1, bf16=True, fp16=False)
+    over = dict(bf16=True, fp16=False) if PRECISION == "bf16" else {}
+    training_class = config.training_class(num_training_steps=1, micro_batch_size=1, gradient_accumulation_steps=1, **over)
     model_class = config.model_class()
     model = model_class.build_model(use_custom_kernels=True)  # the B200 module (the reference passes config.free_lunch)
     dataset = model_class.load_dummy_dataset(num_samples=num_samples, seed=0)
@@ -89,12 +94,20 @@ def run_benchmark(num_nodes: int, gpus_per_node: int, gpu_type: str, model: str,
             continue
         if not tc.runs_on_b200_engine():
             if rank == 0:
-                print(f"[skip] {config}: outside this build's scope (DDP / ZeRO-1 only)", flush=True)
+                print(f"[skip] {config}: outside this build's scope (DDP / ZeRO-1 / ZeRO-2 / FSDP shard_grad_op)", flush=True)
             continue
         r = run_one(config)
         if rank == 0:
-            results.append(dict(config=str(config), **(r or {"micro_batch_size": 0})))
-            print(json.dumps(results[-1]), flush=True)
+            # one row per configuration, the columns scripts/print_optimal_config.py selects (the reference keeps them in its Tango
+            # step cache, experiments/training_time_empirical_sweep.py); appended to a JSON-lines file here
+            row = dict(num_nodes=num_nodes, gpus_per_node=gpus_per_node, gpu_type=gpu_type, model=model, free_lunch=free_lunch,
+                       activation_checkpointing=ckpt, sharding=sharding, offloading=offloading, precision=PRECISION,
+                       **(r or {"micro_batch_size": 0, "training_days": None}))
+            results.append(row)
+            print(json.dumps(row), flush=True)
+            RESULTS_FILE.parent.mkdir(parents=True, exist_ok=True)
+            with open(RESULTS_FILE, "a") as fh:
+                fh.write(json.dumps(row) + "\n")
     if rank == 0 and results:
         best = min((r for r in results if r.get("training_days")), key=lambda r: r["training_days"], default=None)
         print("optimal:", json.dumps(best))
@@ -110,7 +123,10 @@ if __name__ == "__main__":
     ap.add_argument("--gpu-type", required=True)
     ap.add_argument("--model", required=True)
     ap.add_argument("--methods", default="all", choices=["naive", "free-lunch", "all"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "reference"])
+    ap.add_argument("--results-file", type=Path, default=RESULTS_FILE)
     a = ap.parse_args()
+    PRECISION, RESULTS_FILE = a.precision, a.results_file
     try:
         run_benchmark(a.num_nodes, a.gpus_per_node, a.gpu_type, a.model, a.methods)
     except KeyboardInterrupt:

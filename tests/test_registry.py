@@ -89,9 +89,13 @@ def test_hyperparameters_follow_reference():
     assert (r.batch_size, r.training_steps, r.max_grad_norm, r.vocab_size, r.sequence_length) == (8192, 500000, 0.0, 50265, 512)
     with pytest.raises(NotImplementedError):
         get_model_class("mamba")
-    for sharding in ("zero_2", "fsdp_full_shard"):
+    for sharding in ("zero_3", "fsdp_full_shard", "fsdp_hybrid_shard"):  # parameter sharding: out of scope
         tc = TrainingConfig(1, 8, "b200", "pythia-1b", sharding=sharding).training_class()
         assert tc.is_valid() and not tc.runs_on_b200_engine()
+    for sharding in ("", "zero_1", "zero_2", "fsdp_shard_grad_op"):  # DDP, ZeRO-1, gradient sharding: built
+        tc = TrainingConfig(1, 8, "b200", "pythia-1b", sharding=sharding).training_class()
+        assert tc.is_valid() and tc.runs_on_b200_engine()
+    assert not TrainingConfig(1, 8, "b200", "pythia-1b", sharding="zero_2", offloading=True).training_class().runs_on_b200_engine()
 
 
 def test_flop_metric_closed_form():
@@ -167,9 +171,39 @@ def test_registry_matches_the_live_reference_registry():
         for a in attrs:
             mine, theirs = getattr(ours, a), getattr(ref, a)
             assert str(getattr(mine, "value", mine)) == str(getattr(theirs, "value", theirs)), (name, a, mine, theirs)
-        assert ours.optimizer is {torch.optim.Adam: B200Adam, torch.optim.AdamW: B200AdamW}[ref.optimizer], name
+        # the registry hands out the reference's own class; the trainer maps it onto the fused equivalent for a B200 module
+        assert ours.optimizer is ref.optimizer, name
+        from multimodal_llm_pretraining_b200.optim import fused_optimizer_class
+        assert fused_optimizer_class(ours.optimizer) is {torch.optim.Adam: B200Adam, torch.optim.AdamW: B200AdamW}[ref.optimizer], name
     # the synthetic dataset: same constructor arguments, item keys, dtypes and shapes (src/benchmarking/data.py:8-21)
     ref_ds = RefDataset(vocab_size=50304, sequence_length=2049, num_samples=8)
     our_ds = get_model_class("pythia-70m").load_dummy_dataset(num_samples=8, seed=0)
     assert len(ref_ds) == len(our_ds) == 8
     assert {k: (v.dtype, v.shape) for k, v in ref_ds[0].items()} == {k: (v.dtype, v.shape) for k, v in our_ds[0].items()}
+
+
+def test_print_optimal_config_table(tmp_path):
+    """scripts/print_optimal_config.py:8-48 of the reference: rows of one (nodes, gpus, gpu type, model), sorted by training days,
+    with grad_acc_steps = batch_size // (micro_batch_size * gpus_per_node); same columns in the same order."""
+    import json
+    import sys as _sys
+
+    _sys.path.insert(0, str(ROOT / "scripts"))
+    import print_optimal_config as P
+
+    rows = [
+        dict(num_nodes=1, gpus_per_node=8, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=False, sharding="zero_1", offloading=False, micro_batch_size=16, training_days=2.41),
+        dict(num_nodes=1, gpus_per_node=8, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=True, sharding="", offloading=False, micro_batch_size=64, training_days=3.3),
+        dict(num_nodes=1, gpus_per_node=8, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=False, sharding="", offloading=False, micro_batch_size=16, training_days=2.38),
+        dict(num_nodes=1, gpus_per_node=8, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=False, sharding="", offloading=False, micro_batch_size=16, training_days=2.37),  # re-run replaces
+        dict(num_nodes=1, gpus_per_node=8, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=False, sharding="zero_3", offloading=False, micro_batch_size=0, training_days=None),
+        dict(num_nodes=1, gpus_per_node=4, gpu_type="b200", model="pythia-1b", free_lunch=True, activation_checkpointing=False, sharding="", offloading=False, micro_batch_size=16, training_days=4.7),
+    ]
+    f = tmp_path / "r.jsonl"
+    f.write_text("\n".join(json.dumps(r) for r in rows))
+    t = P.optimal_config_table(P.load_results(f), 1, 8, "b200", "pythia-1b")
+    assert list(t[0]) == ["num_nodes", "gpus_per_node", "gpu_type", "model", "free_lunch", "activation_checkpointing", "sharding", "offloading",
+                          "micro_batch_size", "grad_acc_steps", "training_days"]
+    assert [r["training_days"] for r in t] == [2.37, 2.41, 3.3]
+    assert [r["grad_acc_steps"] for r in t] == [8, 8, 2]  # 1024 // (mbs * 8)
+    assert "grad_acc_steps" in P.format_table(t) and P.format_table([]).startswith("(no benchmarked")
