@@ -684,7 +684,10 @@ static void fill_params(const b200_gemm_args* a, GemmParams& p) {
 // (perf triage only).
 static void choose_raster(const b200_gemm_args* a, GemmParams& p, int tile_m) {
     static const int env_group = getenv("B200_GEMM_GROUP_M") ? atoi(getenv("B200_GEMM_GROUP_M")) : -1;
-    static const int env_hints = getenv("B200_GEMM_HINTS") ? atoi(getenv("B200_GEMM_HINTS")) : 1;
+    // hints are OFF by default: measured on the full step they cost 1.5-2 % (EVICT_FIRST lets an A line go before the last of the
+    // CTAs sharing it has read it; the LM head with A pinned doubled its DRAM reads) while the raster alone gained 1.2 %
+    // (profiles/r02_gemm_raster_ab.txt)
+    static const int env_hints = getenv("B200_GEMM_HINTS") ? atoi(getenv("B200_GEMM_HINTS")) : 0;
     const double a_bytes = 2.0 * a->M * a->K, b_bytes = 2.0 * a->N * a->K;
     const double panel_a = 2.0 * tile_m * a->K / (p.split_k > 0 ? p.split_k : 1);
     constexpr double L2_RESIDENT = 40e6;  // what can be expected to stay in the 126 MB L2 next to a streaming operand
