@@ -105,10 +105,12 @@ int b200_cross_entropy(void* logits, const int64_t* labels, float* row_loss, con
 int b200_mean_loss(const float* row_loss, const int* n_valid, int T, float* loss_out, b200_stream_t stream);
 
 /* ---------------------------------------------------------------- Column sums (bias gradients)
- * out[c] += sum_r x[r, c]  (x bf16 [rows, ld]); replaces the bias-grad reduction autograd performs for nn.Linear. */
+ * out[c] += s * sum_r x[r, c]  (x bf16 [rows, ld]); replaces the bias-grad reduction autograd performs for nn.Linear.
+ * out2 (nullable, fp32 [cols]) receives the same increment: two biases fed by one upstream gradient (attention.dense and
+ * mlp.dense_4h_to_h of a parallel-residual GPT-NeoX block). scale_dev (nullable device fp32 scalar) = s, else 1. */
 size_t b200_colsum_workspace_bytes(int cols);
-int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, void* workspace,
-                     size_t workspace_bytes, b200_stream_t stream);
+int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, float* out2, const float* scale_dev,
+                     void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
 /* ---------------------------------------------------------------- GEMM on tcgen05 / TMEM / TMA
  * C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )  — replaces nn.Linear fwd / dgrad / wgrad (cuBLAS in the reference

@@ -82,7 +82,7 @@ SIGNATURES = {
     "b200_cross_entropy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200_mean_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_colsum_workspace_bytes": (c_size_t, [c_int]),
-    "b200_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b200_attention_fwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
     "b200_attention_bwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),

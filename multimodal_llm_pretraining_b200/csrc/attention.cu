@@ -684,6 +684,340 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tr && threadIdx.x == 0) g_attn_trace[8005] = clock64(), g_attn_trace[8007] = globaltimer_ns();
 }
 
+// ---- attn_fwd256s_kernel: attn_fwd256_kernel with the softmax of every S tile split over TWO warps per TMEM lane quarter (320
+// threads: warps 0-7 softmax, 8 TMA producer, 9 MMA issuer). Same TMEM / shared-memory plan plus 1 KB for the exchange.
+struct Fwd256SSmem {
+    static constexpr uint32_t OFF_P = 0;  // two P tiles: softmax of block j+1 writes one while P V_j reads the other
+    static constexpr uint32_t OFF_K = 32768;
+    static constexpr uint32_t OFF_V = OFF_K + 3 * 32768;
+    static constexpr uint32_t OFF_BAR = OFF_V + 3 * 32768;
+    static constexpr uint32_t OFF_X = OFF_BAR + 256;  // 1 KB: partial row maxima of the two column halves, [block parity][half][128] bf16
+    static constexpr uint32_t TOTAL = OFF_X + 1024 + 1024;
+};
+
+__global__ void __launch_bounds__(320, 1)
+attn_fwd256s_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnParams p) {
+    using L = Fwd256SSmem;
+    constexpr int D = 256, BN = 64, NSUB = 4, NST = 3;
+    constexpr uint32_t TM_O = 0, TM_S = 256, TM_Q = 384;
+    constexpr uint32_t KV_BYTES = 32768;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sP = smem + L::OFF_P;
+    uint8_t* sK = smem + L::OFF_K;
+    uint8_t* sV = smem + L::OFF_V;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* q_ready = bars;          // 1 (8 warp arrivals)
+    uint64_t* k_full = bars + 1;       // 3
+    uint64_t* k_empty = bars + 4;      // 3
+    uint64_t* v_full = bars + 7;       // 3
+    uint64_t* v_empty = bars + 10;     // 3
+    uint64_t* s_full = bars + 13;      // 2
+    uint64_t* s_free = bars + 15;      // 2 (4 warp arrivals)
+    // p_ready[b]: P buffer b is written (4 warp arrivals). One barrier PER BUFFER: with a single barrier whose phase
+    // alternates per block, the softmax warps can complete P_{j+1} (its S was issued before P V_j) while the issuer still
+    // waits for a late V_j; the barrier is then two phases ahead and a parity wait for phase j never succeeds again (a
+    // deadlock seen once in ~10^6 CTAs). P_{j+2} cannot be written before P V_j retired (o_done), so per buffer the
+    // waiter is never more than one phase behind.
+    uint64_t* p_ready = bars + 17;     // 2
+    uint64_t* o_done = bars + 19;      // 2: o_done[b] = the P V that read P buffer b has retired
+    uint64_t* q_full = bars + 21;      // 1: the Q tile has landed in its staging area (V stages 1 and 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint8_t* sQst = sV + KV_BYTES;     // 64 KB staging of the Q tile on its way to TMEM
+    __nv_bfloat16* xmax = reinterpret_cast<__nv_bfloat16*>(smem + L::OFF_X);  // [2][2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal blocks first
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * 128;
+    const int kv_end = p.causal ? min(p.S, q0 + 128) : p.S;
+    const int n_blocks = (kv_end + BN - 1) / BN;
+    const int col0 = h * static_cast<int>(p.qkv_head_stride);
+    const int row_base = b * p.S;
+    const bool tr = (p.trace == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ||
+                    (p.trace == 2 && blockIdx.x == 0 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1);
+    if (tr && threadIdx.x == 0) g_attn_trace[8000] = clock64(), g_attn_trace[8006] = globaltimer_ns();
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(q_ready, 8);
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_free[s], 8);
+        }
+        mbar_init(&p_ready[0], 8);
+        mbar_init(&p_ready[1], 8);
+        mbar_init(&o_done[0], 1);
+        mbar_init(&o_done[1], 1);
+        mbar_init(q_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_prologue();  // set-up (barriers, TMEM) overlapped the previous kernel's tail; global memory only from here on
+    if (tr && threadIdx.x == 0) g_attn_trace[8001] = clock64();
+
+    if (warp == 8) {
+        // ---------------------------------------------------------------- TMA producer: two in-order rings, served as they free up
+        if (elect_one()) {
+            // Q tile -> staging (full 128-byte lines through TMA; per-thread row loads of a [rows x 512 B] tile took 20k clocks)
+            mbar_expect_tx(q_full, 65536);
+            for (int c = 0; c < NSUB; ++c) tma_load_2d(sQst + c * 16384, &tmQ, q_full, col0 + c * 64, row_base + q0);
+            bool q_moved = false;  // V stages 1 and 2 are free once the softmax warps have copied Q into TMEM
+            int next_k = 0, next_v = 0;
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_k < n_blocks || next_v < n_blocks) {
+                bool progressed = false;
+                if (!q_moved) q_moved = mbar_try_wait(q_ready, 0);
+                if (next_k < n_blocks && mbar_try_wait(&k_empty[next_k % NST], ((next_k / NST) & 1) ^ 1)) {
+                    const int s = next_k % NST;
+                    mbar_expect_tx(&k_full[s], KV_BYTES);
+                    for (int c = 0; c < NSUB; ++c) tma_load_2d(sK + s * KV_BYTES + c * 8192, &tmK, &k_full[s], col0 + c * 64, row_base + next_k * BN);
+                    ++next_k, progressed = true;
+                }
+                if (next_v < n_blocks && (q_moved || next_v % NST == 0) && mbar_try_wait(&v_empty[next_v % NST], ((next_v / NST) & 1) ^ 1)) {
+                    const int s = next_v % NST;
+                    mbar_expect_tx(&v_full[s], KV_BYTES);
+                    for (int c = 0; c < NSUB; ++c) tma_load_2d(sV + s * KV_BYTES + c * 8192, &tmV, &v_full[s], col0 + c * 64, row_base + next_v * BN);
+                    ++next_v, progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention fwd256s producer stalled (block %d,%d,%d k %d v %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, next_k, next_v);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, BN, false, false);  // S = Q K^T (A = Q from TMEM)
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, D, false, true);    // O += P V (V MN-major)
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(sV), 8192, 1024);
+            const uint64_t p_desc = umma_desc_sw128(smem_u32(sP), 16, 1024);
+            auto issue_s = [&](int j) {
+                const int s = j % NST;
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((s * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ts(tmem + TM_S + (j & 1) * BN, tmem + TM_Q + kk * 8, kd + static_cast<uint64_t>(((kk >> 2) * 8192 + (kk & 3) * 32) >> 4), idesc_s, kk != 0);
+                tc_commit(&k_empty[s]);  // K_j is dead as soon as S_j retires
+                tc_commit(&s_full[j & 1]);
+            };
+            auto issue_pv = [&](int j) {
+                const int s = j % NST;
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((s * KV_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk)
+                    umma_ss(tmem + TM_O, p_desc + static_cast<uint64_t>(((j & 1) * 16384 + kk * 32) >> 4), vd + static_cast<uint64_t>((kk * 2048) >> 4), idesc_o,
+                            (j | kk) != 0);
+                tc_commit(&v_empty[s]);
+                tc_commit(&o_done[j & 1]);
+            };
+            mbar_wait(q_ready, 0);
+            tc_fence_after();
+            int next_s = 0, next_pv = 0;  // S_j needs K_j and a free S buffer; P V_j needs P_j and V_j
+            const uint64_t t_start = globaltimer_ns();
+            uint32_t spins = 0;
+            while (next_pv < n_blocks) {
+                bool progressed = false;
+                if (next_s < n_blocks && next_s <= next_pv + 1 && mbar_try_wait(&k_full[next_s % NST], (next_s / NST) & 1) &&
+                    (next_s < 2 || mbar_try_wait(&s_free[next_s & 1], ((next_s >> 1) - 1) & 1))) {
+                    tc_fence_after();
+                    trace_evt(tr, 4096 + 16 * next_s + 0);
+                    issue_s(next_s);
+                    ++next_s, progressed = true;
+                }
+                if (next_pv < next_s && mbar_try_wait(&p_ready[next_pv & 1], (next_pv >> 1) & 1) && mbar_try_wait(&v_full[next_pv % NST], (next_pv / NST) & 1)) {
+                    tc_fence_after();
+                    trace_evt(tr, 4096 + 16 * next_pv + 1);
+                    issue_pv(next_pv);
+                    ++next_pv, progressed = true;
+                }
+                if (!progressed && ((++spins) & 0xfff) == 0 && globaltimer_ns() - t_start > 4 * B200_MBAR_TIMEOUT_NS) {
+                    printf("b200pt: attention fwd256s issuer stalled (block %d,%d,%d s %d pv %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, next_s, next_pv);
+                    __trap();
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- softmax warps 0..7: TWO threads per query row.
+        // Warps w and w + 4 sit on the same SM sub-partition and the same TMEM lane quarter (hardware: lanes 32 * (warp % 4)); warp
+        // w / 4 = hf owns key columns [32 hf, 32 hf + 32) of every 64-key block. The single softmax warp per sub-partition of
+        // attn_fwd256_kernel ran TMEM load -> max -> 64 exp -> pack -> store as ONE dependency chain of ~1900 clocks per block with
+        // nothing to overlap it (measured: a lone CTA takes as long per block as a full grid, profiles/r02_attn_scaling.txt), twice
+        // the 1024 tensor clocks it feeds. Two warps halve the chain and overlap each other's TMEM / MUFU / store latencies. The two
+        // threads of a row must use the SAME reference maximum: each rounds its partial maximum UP to bf16, they swap the 16-bit
+        // values through shared memory (one 64-thread named barrier per block) and both take the larger one — any common reference
+        // within 2^8 of the true maximum is exact for softmax (lazy rescaling), so the rounding costs nothing.
+        const int quad = warp & 3, hf = warp >> 2;
+        const int r = quad * 32 + lane;
+        const int q_idx = q0 + r;
+        const bool row_ok = q_idx < p.S;
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+        const float sl2 = p.scale * LOG2E_F;
+        const int pair_bar = 2 + quad;
+        {
+            // Q row: staging tile (SWIZZLE_128B, 4 sub-tiles of 64 columns) -> registers -> TMEM (16-bit pairs, 128 columns); half each
+            mbar_wait(q_full, 0);
+#pragma unroll
+            for (int cq = 0; cq < 2; ++cq) {
+                const int c = hf * 2 + cq;
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 u = ld_shared_v4(sQst + c * 16384 + sw128_offset(r, i));
+                    v[i * 4 + 0] = u.x, v[i * 4 + 1] = u.y, v[i * 4 + 2] = u.z, v[i * 4 + 3] = u.w;
+                }
+                tmem_st_32x32(lane_addr + TM_Q + c * 32, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+            if (tr && threadIdx.x == 0) g_attn_trace[8002] = clock64();
+        }
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < n_blocks; ++j) {
+            const bool tr0 = tr && threadIdx.x == 0;
+            trace_evt(tr0, 4096 + 16 * j + 8);
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            trace_evt(tr0, 4096 + 16 * j + 9);
+            uint32_t sv[32];
+            tmem_ld_32x32(lane_addr + TM_S + (j & 1) * BN + hf * 32, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[j & 1]);
+            const int kv0 = j * BN + hf * 32;  // first key of this thread's columns
+            if ((j * BN + BN > p.S) || (p.causal && j * BN + BN - 1 > q0)) {
+                const int lim = p.causal ? min(p.S - 1, q_idx) : p.S - 1;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sv[i] = (kv0 + i > lim) ? 0xff800000u : sv[i];
+            }
+            float mx = __uint_as_float(sv[0]);
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            // common row maximum of both halves: bf16 values rounded towards +inf, so both threads compute the identical number
+            const __nv_bfloat16 mine = __float2bfloat16_ru(mx * sl2);
+            xmax[((j & 1) * 2 + hf) * 128 + r] = mine;
+            named_bar_sync(pair_bar, 64);
+            mx = fmaxf(__bfloat162float(mine), __bfloat162float(xmax[((j & 1) * 2 + (hf ^ 1)) * 128 + r]));
+            const float m_new = fmaxf(m_used, mx);
+            const bool need = m_new > m_used + 8.0f;  // lazy rescale: only when the running max grew by > 2^8 (same verdict in both halves)
+            // P buffer j & 1 was last read by P V_{j-2}
+            trace_evt(tr0, 4096 + 16 * j + 10);
+            if (j >= 2) mbar_wait(&o_done[j & 1], ((j >> 1) - 1) & 1);
+            trace_evt(tr0, 4096 + 16 * j + 11);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                // rescaling O races with an in-flight P V: wait for the latest one (rare: the max must grow by > 2^8). Each half
+                // rescales its four 32-column chunks of the row's accumulator; P V_j is issued only after all eight warps arrive.
+                mbar_wait(&o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                {
+                    const float alpha = need ? ex2(m_used - m_new) : 1.0f;
+                    l *= alpha;
+#pragma unroll 1
+                    for (int c = hf * 4; c < hf * 4 + 4; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(lane_addr + TM_O + c * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st_32x32(lane_addr + TM_O + c * 32, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            if (need) m_used = m_new;
+            const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = ex2(fmaf(__uint_as_float(sv[cc * 8 + i]), sl2, neg_m));
+                    sum += e[i];
+                }
+                st_shared_v4(sP + (j & 1) * 16384 + sw128_offset(r, hf * 4 + cc), make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
+            }
+            l += sum;  // partial denominator of this thread's columns; the halves meet in the epilogue
+            trace_evt(tr0, 4096 + 16 * j + 12);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[j & 1]);
+            trace_evt(tr0, 4096 + 16 * j + 13);
+        }
+        // ---- epilogue: O / l -> 16-bit, LSE. Every loop read of xmax is over once the last P V has retired (it needs all eight
+        // p_ready arrivals), so the same 1 KB now carries the two partial denominators as fp32.
+        if (tr && threadIdx.x == 0) g_attn_trace[8003] = clock64();
+        mbar_wait(&o_done[(n_blocks - 1) & 1], ((n_blocks - 1) >> 1) & 1);
+        tc_fence_after();
+        float* xl = reinterpret_cast<float*>(smem + L::OFF_X);  // [2][128]
+        xl[hf * 128 + r] = l;
+        named_bar_sync(pair_bar, 64);
+        l += xl[(hf ^ 1) * 128 + r];
+        const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+        const bool tma_out = (p.S % 128) == 0;  // whole 128-row boxes: stage O in the (idle) K ring and TMA-store full lines
+        elem_t* orow = p.o + static_cast<size_t>(row_base + q_idx) * p.o_row_stride + static_cast<size_t>(h) * p.o_head_stride;
+#pragma unroll 1
+        for (int c = hf * 4; c < hf * 4 + 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_addr + TM_O + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+                o.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+                o.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+                o.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+                if (tma_out) st_shared_v4(sK + (c >> 1) * 16384 + sw128_offset(r, (c & 1) * 4 + g), o);
+                else if (row_ok) st_v4(orow + c * 32 + g * 8, o);
+            }
+        }
+        if (tma_out) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 256);
+            if (threadIdx.x == 0) {
+                for (int c = 0; c < NSUB; ++c) tma_store_2d(&tmO, sK + c * 16384, h * static_cast<int>(p.o_head_stride) + c * 64, row_base + q0);
+                tma_store_commit();
+                tma_store_wait_read<0>();  // shared memory must outlive the bulk stores READING it; the writes drain on their own
+            }
+        }
+        if (row_ok && hf == 0) p.lse[(static_cast<size_t>(b) * p.H + h) * p.S + q_idx] = (m_used + log2f(l)) * LN2_F;
+        tc_fence_before();
+        if (tr && threadIdx.x == 0) g_attn_trace[8004] = clock64();
+    }
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+    if (tr && threadIdx.x == 0) g_attn_trace[8005] = clock64(), g_attn_trace[8007] = globaltimer_ns();
+}
+
 // =================================================================================================================
 // backward
 // =================================================================================================================
@@ -1577,6 +1911,22 @@ static int launch_fwd256(const b200_attn_args* a, cudaStream_t st) {
     return check_launch("attention_fwd256");
 }
 
+static int launch_fwd256s(const b200_attn_args* a, cudaStream_t st) {
+    using L = Fwd256SSmem;
+    static_assert(L::TOTAL <= 232448, "fwd256s smem budget");
+    CUtensorMap tq, tk, tv, to;
+    int rc;
+    if ((rc = qkv_tmap(&tq, a->q, a, a->qkv_row_stride, a->qkv_head_stride, 128))) return rc;
+    if ((rc = qkv_tmap(&tk, a->k, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    if ((rc = qkv_tmap(&tv, a->v, a, a->qkv_row_stride, a->qkv_head_stride, 64))) return rc;
+    if ((rc = qkv_tmap(&to, a->o, a, a->o_row_stride, a->o_head_stride, 128))) return rc;
+    auto kern = attn_fwd256s_kernel;
+    if ((rc = set_smem(kern, L::TOTAL, "attention_fwd256s"))) return rc;
+    dim3 grid((a->S + 127) / 128, a->H, a->B);
+    launch_k(kern, dim3(grid), dim3(320), L::TOTAL, st, tq, tk, tv, to, make_params(a));
+    return check_launch("attention_fwd256s");
+}
+
 template <int D, int DH, int STAGES, bool DKV, int SBUF, bool DROP>
 static int launch_bwd_impl(const b200_attn_args* a, cudaStream_t st, bool store_scores) {
     using L = BwdSmem<D, STAGES, DKV, SBUF>;
@@ -1697,7 +2047,9 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: {
             static const bool old_fwd = getenv("B200_ATTN_OLD_FWD") != nullptr;  // perf triage only
-            return (old_fwd || a->dropout_p > 0.f) ? launch_fwd<256, 64, 2>(a, st) : launch_fwd256(a, st);
+            static const bool one_warp = getenv("B200_ATTN_FWD256_1WARP") != nullptr;  // perf triage only: round-1 softmax layout
+            if (old_fwd || a->dropout_p > 0.f) return launch_fwd<256, 64, 2>(a, st);
+            return one_warp ? launch_fwd256(a, st) : launch_fwd256s(a, st);
         }
     }
 }

@@ -258,13 +258,16 @@ colsum_partial_kernel(const elem_t* __restrict__ x, int rows, int cols, int64_t 
     }
 }
 __global__ void __launch_bounds__(256)
-colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ out) {
+colsum_finalize_kernel(const float* __restrict__ partial, int n_partial, int cols, float* __restrict__ out, float* __restrict__ out2,
+                       const float* __restrict__ scale) {
     pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     float t = 0.f;
     for (int p = 0; p < n_partial; ++p) t += partial[static_cast<size_t>(p) * cols + c];
+    if (scale) t *= *scale;
     out[c] += t;
+    if (out2) out2[c] += t;  // two biases that share one upstream gradient (attention.dense and mlp.dense_4h_to_h of a GPT-NeoX block)
 }
 
 
@@ -413,8 +416,8 @@ extern "C" int b200_scale_f32(float* x, size_t n, const float* scale_dev, float 
 }
 
 extern "C" size_t b200_colsum_workspace_bytes(int cols) { return static_cast<size_t>(64) * cols * sizeof(float); }
-extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, void* workspace,
-                                size_t workspace_bytes, b200_stream_t stream) {
+extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, float* out2, const float* scale_dev,
+                                void* workspace, size_t workspace_bytes, b200_stream_t stream) {
     B200_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && aligned16(x), "colsum: cols/ld must be multiples of 8 and x 16B aligned");
     B200_REQUIRE(workspace_bytes >= b200_colsum_workspace_bytes(cols), "colsum: workspace too small");
     const int col_blocks = (cols + 255) / 256;
@@ -428,7 +431,7 @@ extern "C" int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, f
     launch_k(colsum_partial_kernel, dim3(col_blocks, chunks), dim3(256), 0, as_stream(stream), static_cast<const elem_t*>(x), rows, cols, ld, rows_per_chunk, part);
     int rc = check_launch("colsum_partial");
     if (rc) return rc;
-    launch_k(colsum_finalize_kernel, dim3((cols + 255) / 256), dim3(256), 0, as_stream(stream), part, chunks, cols, out);
+    launch_k(colsum_finalize_kernel, dim3((cols + 255) / 256), dim3(256), 0, as_stream(stream), part, chunks, cols, out, out2, scale_dev);
     return check_launch("colsum_finalize");
 }
 

@@ -77,14 +77,6 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     tn = r / gm;
 }
 
-template <int BN, int STAGES>
-constexpr size_t gemm_smem_bytes() {
-    // ring + barriers (256) + bias [2][BN] fp32 + two 16 KB output slabs + alignment slack; the 227 KB per-CTA limit
-    // (232448 B) leaves 256 B of slack less than a full 1 KB for BN=256 — the kernel traps if the base is that unlucky.
-    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 256 + 2 * BN * 4 + 32768;
-    return need + 1024 <= 232448 ? need + 1024 : 232448;
-}
-
 // `side` = the 32-column slice of the residual / dgelu_in row, prefetched one chunk ahead so that its global-load latency
 // overlaps the previous chunk's math; `sbias` = this tile's bias staged in shared memory (one coalesced load per tile).
 // With p.tma_store the bf16 results go to the 128-row x 64-column SWIZZLE_128B staging slab in shared memory
@@ -180,7 +172,7 @@ struct GemmGeom {
     static constexpr int TILE_M = GEMM_BM * CG;  // output rows per tile (per CTA pair when CG = 2)
 };
 
-// smem per CTA: ring of STAGES x (A 16 KB + B (BN/CG) x 128 B) + two 16 KB output slabs + barriers + bias [2][BN]
+// smem per CTA: ring of STAGES x (A 16 KB + B (BN/CG) x 128 B) + two 16 KB output slabs + barriers + bias [BN] + 1 KB alignment slack
 template <int EPI, int SIDE>
 constexpr uint32_t gemm_stage_bytes() {
     // per epilogue group: one 16 KB output slab, plus one for the pre-GELU aux output (EPI 1) or to double-buffer the
@@ -189,7 +181,7 @@ constexpr uint32_t gemm_stage_bytes() {
 }
 template <int BN, int STAGES, int CG, int EPI, int SIDE>
 constexpr size_t gemm_smem_bytes_cg() {
-    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<EPI, SIDE>();
+    constexpr size_t need = static_cast<size_t>(STAGES) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + BN * 4 + gemm_stage_bytes<EPI, SIDE>();
     return need + 1024 <= 232448 ? need + 1024 : 232448;
 }
 
@@ -221,10 +213,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tempty = bars + 2 * STAGES + 2;
     uint64_t* side_full = bars + 2 * STAGES + 4;  // [2 groups][2 buffers] (SIDE only)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
-    float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + STG + 256);  // [2][BN]
+    float* sbias = reinterpret_cast<float*>(smem + RING_BYTES + STG + 256);  // [BN]
     static_assert(RING_BYTES % 1024 == 0, "staging slabs must be 1024B aligned");
     static_assert((2 * STAGES + 9) * 8 <= 256, "barrier block overflow");
-    if (threadIdx.x == 0 && (smem + RING_BYTES + STG + 256 + 2 * BN * 4) > (smem_raw + gemm_smem_bytes_cg<BN, STAGES, CG, EPI, SIDE>())) {
+    if (threadIdx.x == 0 && (smem + RING_BYTES + STG + 256 + BN * 4) > (smem_raw + gemm_smem_bytes_cg<BN, STAGES, CG, EPI, SIDE>())) {
         printf("b200pt gemm: dynamic smem base misaligned beyond slack\n");
         __trap();
     }
@@ -415,10 +407,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int row = row0 + quarter * 32 + lane;
             const int n0 = tn * BN;
             const int c_m0 = row0 + zb * p.c_m_b + zh * p.c_m_h, c_n0 = n0 + zb * p.c_n_b + zh * p.c_n_h;
-            float* sb = sbias + as * BN;
+            float* sb = sbias;
             if (p.bias) {
-                // buffer `as` was last read two tiles ago; every epilogue warp has passed the barrier of the tile in
-                // between, so it is free. One coalesced load per tile replaces 32 dependent L1 round trips per thread.
+                // ONE bias buffer (a second one cost the 1 KB that the alignment slack of the 5-stage fused variants needs): every
+                // epilogue warp must be done reading the previous tile's bias before it is overwritten, hence the barrier in front.
+                // One coalesced load per tile replaces 32 dependent L1 round trips per thread.
+                asm volatile("bar.sync 3, 256;" ::: "memory");
                 for (int i = et_all; i < BN; i += 256) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
                 asm volatile("bar.sync 3, 256;" ::: "memory");
             }
@@ -557,15 +551,15 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1,
     return 0;
 }
 
-// The fused-epilogue variants carry 64 KB of slabs. With CTA pairs (32 KB stages) five stages + slabs + barriers + bias come to
-// 231 680 B, 768 B under the 227 KB limit: no room for the full 1 KB of alignment slack, but the dynamic shared window of a
-// kernel without static shared memory starts 1 KB-aligned (the kernel traps with a message if it ever does not). Four stages
-// hold only 128 KB in flight, marginal against a ~2000-clock TMA latency at 64 B/clk per SM (the 4-stage plain GEMM measured
-// 3 % slower than the 5-stage one).
+// The fused-epilogue variants carry 64 KB of slabs. With CTA pairs (32 KB stages) five stages + slabs + barriers + ONE bias
+// buffer come to 230 656 B; with the full 1 KB of alignment slack 231 680 B <= the 232 448 B per-CTA limit, so the layout holds for
+// ANY alignment of the dynamic shared window (round 1 kept two bias buffers, had no room for the slack and relied on the window
+// starting 1 KB-aligned). Four stages hold only 128 KB in flight, marginal against a ~2000-clock TMA latency at 64 B/clk per SM
+// (the 4-stage plain GEMM measured 3 % slower than the 5-stage one).
 template <int BN, int STAGES, int CG>
 constexpr int gelu_stages() {
     int st = STAGES;
-    while (static_cast<size_t>(st) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + 2 * BN * 4 + gemm_stage_bytes<1, 0>() > 232448) --st;
+    while (static_cast<size_t>(st) * (GEMM_BM * GEMM_BK * 2 + (BN / CG) * GEMM_BK * 2) + 256 + BN * 4 + gemm_stage_bytes<1, 0>() + 1024 > 232448) --st;
     return st;
 }
 

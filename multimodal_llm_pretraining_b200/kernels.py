@@ -187,13 +187,15 @@ def cross_entropy_(logits, labels, V=None, ignore_index=-100, write_grad=True, g
     return loss, n_valid
 
 
-def colsum_(x, out):
-    """out[c] (fp32) += sum_r x[r, c] for bf16 x [rows, cols]."""
+def colsum_(x, out, out2=None, scale=None):
+    """out[c] (fp32) += s * sum_r x[r, c] for bf16 x [rows, cols]; out2 (optional) gets the same increment; scale = device fp32 scalar s."""
+    _req(out2 is None or (out2.dtype == F32 and out2.numel() == out.numel()), "colsum: bad out2")
+    _req(scale is None or (scale.dtype == F32 and scale.numel() == 1), "colsum: scale must be a device fp32 scalar")
     _req(x.dtype in HALF and x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32 and out.numel() == x.shape[1], "colsum: bad tensors")
     lib = _L(x)
     rows, cols = x.shape
     ws = _workspace(x.device, lib.b200_colsum_workspace_bytes(cols))
-    check(lib.b200_colsum_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), ptr(ws), ws.numel(), stream_ptr()), "b200_colsum_bf16")
+    check(lib.b200_colsum_bf16(ptr(x), rows, cols, x.stride(0), ptr(out), ptr(out2), ptr(scale), ptr(ws), ws.numel(), stream_ptr()), "b200_colsum_bf16")
     _count(2)
     return out
 

@@ -298,8 +298,8 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         T = B * S
         # --- MLP branch: y = W2 gelu(W1 a2 + b1) + b2
         K.gemm(dy, g, a_mn=True, b_mn=True, out=self._g(f"{p}.mlp.dense_4h_to_h.weight"), accumulate=True)
-        dy_colsum = K.colsum_(dy, torch.zeros(h, dtype=torch.float32, device=dy.device))  # shared by both output biases
-        self._g(f"{p}.mlp.dense_4h_to_h.bias").add_(dy_colsum)
+        # both output biases of the parallel-residual block see the same upstream gradient: one column-sum pass, two accumulators
+        K.colsum_(dy, self._g(f"{p}.mlp.dense_4h_to_h.bias"), out2=self._g(f"{p}.attention.dense.bias"))
         dh1 = K.gemm(dy, self._w(f"{p}.mlp.dense_4h_to_h.weight"), b_mn=True, dgelu_in=h1)
         K.gemm(dh1, a2, a_mn=True, b_mn=True, out=self._g(f"{p}.mlp.dense_h_to_4h.weight"), accumulate=True)
         K.colsum_(dh1, self._g(f"{p}.mlp.dense_h_to_4h.bias"))
@@ -308,7 +308,6 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         # --- attention branch
         o2 = o.view(T, h)
         K.gemm(dy, o2, a_mn=True, b_mn=True, out=self._g(f"{p}.attention.dense.weight"), accumulate=True)
-        self._g(f"{p}.attention.dense.bias").add_(dy_colsum)
         d_o = K.gemm(dy, self._w(f"{p}.attention.dense.weight"), b_mn=True)
         dqkv = torch.empty_like(qkv)
         q5, d5 = qkv.view(B, S, nh, 3, hd), dqkv.view(B, S, nh, 3, hd)

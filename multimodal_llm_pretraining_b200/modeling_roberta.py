@@ -361,9 +361,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         g_dec = f.gview_alloc("roberta.embeddings.word_embeddings.weight")
         K.gemm(dl, n, a_mn=True, b_mn=True, out=g_dec, accumulate=True, alpha=alpha)
         # decoder bias grad = alpha * colsum(dlogits)
-        bsum = torch.zeros(self.Vp, dtype=torch.float32, device=dl.device)
-        K.colsum_(dl, bsum)
-        f.gview_alloc("lm_head.bias").add_(bsum * alpha)
+        K.colsum_(dl, f.gview_alloc("lm_head.bias"), scale=alpha)
         dn = K.gemm(dl, f.view_alloc(f.shadow, "roberta.embeddings.word_embeddings.weight"), b_mn=True, alpha=alpha)
         ctx.dlogits = None
         dd = K.layernorm_bwd(d, mean, rstd, self._p("lm_head.layer_norm.weight"), dn,

@@ -2,8 +2,12 @@
  (a) the golden vectors of the real HF module (tests/golden/neox_tiny.pt),
  (b) the fp32 CPU oracle on other shapes (head_dim 128 / 256),
  (c) the live HF module trained side by side for 200 steps (loss curve within 1 %, north_star).
-Tolerances are vs fp32 references; bf16 operands => rel <= 2e-2 per tensor (5e-2 for whole-model parameter gradients,
-where per-kernel roundings compound through the depth)."""
+Tolerances are vs fp32 references; bf16 operands => rel <= 2e-2 per tensor (north_star), whole-model parameter gradients included.
+The one exception is stated where it applies: the key third of query_key_value.bias has an analytically ZERO gradient (softmax is
+invariant to a per-query shift of the scores), so HF holds rounding noise there and so do we; it is compared on the query and value
+thirds only. After three Adam steps the parameter UPDATE is compared: Adam's first steps move every element by ~lr * sign(g), so
+elements whose gradient is smaller than the bf16 rounding of the backward pass take opposite +-lr steps; the bound per tensor is
+stated in the test and the measured values are printed."""
 import sys
 from pathlib import Path
 from types import SimpleNamespace
@@ -61,8 +65,15 @@ def test_loss_and_grads_vs_hf_golden(gold, dev):
     assert abs(out.loss.item() - gold["loss0"]) <= 2e-3 * gold["loss0"], (out.loss.item(), gold["loss0"])
     out.loss.backward()
     grads = {n: p.grad for n, p in m.named_parameters()}
+    worst = (0.0, None)
     for k, g in gold["grads"].items():
-        assert rel(grads[k], g) <= 5e-2, (k, rel(grads[k], g))
+        a, b = grads[k], g
+        if k.endswith("query_key_value.bias"):  # [nh, 3, hd]: drop the key third (analytically zero gradient, see module docstring)
+            nh = gold["cfg"]["num_attention_heads"]
+            a, b = a.view(nh, 3, -1)[:, [0, 2]], g.view(nh, 3, -1)[:, [0, 2]]
+        worst = max(worst, (rel(a, b), k))
+        assert rel(a, b) <= 2e-2, (k, rel(a, b))
+    print("whole-model gradients vs HF fp32 golden: worst rel err %.3e (%s), tolerance 2e-2" % worst)
     for k, n in gold["grad_norms"].items():
         got = grads[k].norm().item()
         assert abs(got - n) <= 5e-2 * n + 1e-6, (k, got, n)
@@ -87,11 +98,20 @@ def test_three_adam_steps_vs_hf_golden(gold, dev):
     for a, b in zip(norms, gold["clip_norms"]):
         assert abs(a - b) <= 5e-2 * b, (norms, gold["clip_norms"])
     sd = m.state_dict()
+    errs = []
     for k, v in gold["params_after3"].items():
         # 3 Adam steps move each weight by ~3*lr; compare the UPDATE, not the weight
         upd_ref = v - gold["state_dict"][k]
         upd_got = sd[k].cpu() - gold["state_dict"][k]
-        assert rel(upd_got, upd_ref) <= 0.15, (k, rel(upd_got, upd_ref))
+        if k.endswith("query_key_value.bias"):
+            nh = gold["cfg"]["num_attention_heads"]
+            upd_ref, upd_got = upd_ref.view(nh, 3, -1)[:, [0, 2]], upd_got.view(nh, 3, -1)[:, [0, 2]]
+        errs.append((rel(upd_got, upd_ref), k))
+    errs.sort(reverse=True)
+    print("3-step Adam update vs HF fp32 golden, worst tensors:", [(k, round(e, 4)) for e, k in errs[:5]])
+    for e, k in errs:
+        # sign flips of near-zero gradients under Adam's ~lr*sign(g) first steps; a wrong update rule or a stale moment gives O(1)
+        assert e <= 0.1, (k, e)
 
 
 @pytest.mark.parametrize("nh,h", [(2, 256), (1, 256), (4, 320)])  # head_dim 128, 256, 80 (Pythia-1.4b / 1b / 2.8b head shapes)
@@ -105,8 +125,14 @@ def test_loss_and_grads_vs_oracle_other_head_dims(dev, nh, h):
     loss = m(input_ids=ids.to(dev), labels=ids.to(dev)).loss
     loss.backward()
     assert abs(loss.item() - ref_loss.item()) <= 2e-3 * ref_loss.item()
+    worst = (0.0, None)
     for n, p in m.named_parameters():
-        assert rel(p.grad, ref_grads[n]) <= 5e-2, (n, rel(p.grad, ref_grads[n]))
+        a, b = p.grad, ref_grads[n]
+        if n.endswith("query_key_value.bias"):
+            a, b = a.view(nh, 3, -1)[:, [0, 2]], b.view(nh, 3, -1)[:, [0, 2]]
+        worst = max(worst, (rel(a, b), n))
+        assert rel(a, b) <= 2e-2, (n, rel(a, b))
+    print("head_dim %d gradients vs the fp32 oracle: worst rel err %.3e (%s), tolerance 2e-2" % ((h // nh,) + worst))
 
 
 def test_grad_accumulation_checkpointing_and_torch_optimizer_interop(gold, dev):
