@@ -2047,9 +2047,13 @@ extern "C" int b200_attention_fwd(const b200_attn_args* a, b200_stream_t stream)
         case 128: return launch_fwd<128, 128, 2>(a, st);
         default: {
             static const bool old_fwd = getenv("B200_ATTN_OLD_FWD") != nullptr;  // perf triage only
-            static const bool one_warp = getenv("B200_ATTN_FWD256_1WARP") != nullptr;  // perf triage only: round-1 softmax layout
+            // B200_ATTN_FWD256_SPLIT=1: the variant with two softmax warps per TMEM lane quarter (attn_fwd256s_kernel). Measured
+            // equal to the one-warp layout (0.306 vs 0.310 ms per layer, step 186.1 k vs 185.6 k tokens/s, profiles/
+            // r02_attention_fwd256_analysis.txt): both warps of a pair sit on the same SM sub-partition and share its MUFU unit,
+            // and the exp phase (64 ex2 per row per block = 512 MUFU clocks) is 680 of the 1400-clock per-block chain either way.
+            static const bool split = getenv("B200_ATTN_FWD256_SPLIT") != nullptr;
             if (old_fwd || a->dropout_p > 0.f) return launch_fwd<256, 64, 2>(a, st);
-            return one_warp ? launch_fwd256(a, st) : launch_fwd256s(a, st);
+            return split ? launch_fwd256s(a, st) : launch_fwd256(a, st);
         }
     }
 }
