@@ -120,7 +120,7 @@ int b200_colsum_bf16(const void* x, int rows, int cols, int64_t ld, float* out, 
  *   fwd   y = x W^T      : a_mn 0, b_mn 0 (W [out,in])
  *   dgrad dx = dy W      : a_mn 0, b_mn 1
  *   wgrad dW = dy^T x    : a_mn 1, b_mn 1, c_fp32 = 1, accumulate = 1
- * epilogue order: acc*alpha -> +bias[n] -> gelu -> +residual[m,n] -> (+C if accumulate) -> store (bf16 or fp32).
+ * epilogue order: acc*alpha -> +bias[n] -> gelu -> dropout -> +residual[m,n] -> (+C if accumulate) -> store (bf16 or fp32).
  * aux_out (nullable, bf16 [M,N], ld = ldc): receives the value BEFORE gelu (pre-activation kept for backward).
  * dgelu_in (nullable, bf16 [M,N], ld = ldr): value is multiplied by gelu'(dgelu_in[m,n]) (fused dGELU for dgrad). */
 typedef struct b200_gemm_args {
@@ -142,6 +142,12 @@ typedef struct b200_gemm_args {
     const float* alpha_dev; /* device fp32 scalar or NULL (=1) */
     void* aux_out;          /* bf16 or NULL */
     const void* dgelu_in;   /* bf16 or NULL */
+    /* fused nn.Dropout in front of the residual add (RoBERTa: LN(dropout(dense(x)) + residual), HF:models/roberta/
+     * modeling_roberta.py:339-341,397-399): C = dropout(alpha * A B^T + bias) + residual with b200_dropout's mask of
+     * (dropout_seed, flat element index m * ldc + n), so b200_dropout(grad, seed) is its backward. Needs `residual`;
+     * dropout_p = 0 is off. */
+    float dropout_p;
+    uint64_t dropout_seed;
 } b200_gemm_args;
 int b200_gemm_bf16(const b200_gemm_args* args, b200_stream_t stream);
 

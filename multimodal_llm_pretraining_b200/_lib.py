@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("alpha_dev", c_void_p),
         ("aux_out", c_void_p),
         ("dgelu_in", c_void_p),
+        ("dropout_p", c_float), ("dropout_seed", C.c_uint64),
     ]
 
 

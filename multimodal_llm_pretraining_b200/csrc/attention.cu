@@ -72,24 +72,35 @@ struct AttnParams {
     elem_t* ds_out;  // dV = P^T dO and dK = dS^T Q can run as batched GEMMs (head_dim 256, see file header)
 };
 
-// Dropout mask of score element (q, k) of head bh: the 16-bit lane (q & 1) * 2 + (k & 1) of one 64-bit hash per 2 x 2 block of
-// the [S, S] score matrix. Forward (thread = query row, walks keys) and both backward passes (thread = query or key row)
-// recompute the same bits; a 2 x 2 grouping costs half a hash per element whichever way a thread walks.
-__device__ __forceinline__ uint64_t attn_mix64(uint64_t x) {
-    x ^= x >> 30;
-    x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27;
-    x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
+// Dropout mask of score element (q, k) of head bh: 16-bit lane (k & 1) of ONE 32-bit counter hash per (query, key pair):
+//   idx = ((bh * S + q) * ceil(S / 2) + (k >> 1)) mod 2^32,   x = lowbias32-style mix of idx with the two halves of the seed.
+// Forward and the dQ pass (thread = query row, walks keys) pay one hash per two elements, the dK/dV pass (thread = key row, walks
+// queries) one per element. Round 1 used a 64-bit splitmix hash per 2 x 2 block: ~30 integer instructions per hash made the
+// dropout forward 3x slower than the dropout-free one (RoBERTa-large: 624 vs ~215 us per layer); this one is 9.
+struct DropKey {
+    uint32_t s0, s1;
+};
+__device__ __forceinline__ DropKey attn_drop_key(unsigned long long seed) {
+    DropKey k;
+    k.s0 = static_cast<uint32_t>(seed) * 0x9E3779B1u + 0x85EBCA6Bu;
+    k.s1 = static_cast<uint32_t>(seed >> 32) ^ 0xC2B2AE35u;
+    return k;
+}
+__device__ __forceinline__ uint32_t attn_drop_row(int bh, int S, int q) {  // (bh * S + q) * ceil(S / 2), wrapping
+    return (static_cast<uint32_t>(bh) * static_cast<uint32_t>(S) + static_cast<uint32_t>(q)) * static_cast<uint32_t>((S + 1) >> 1);
+}
+__device__ __forceinline__ uint32_t attn_drop_hash(DropKey key, uint32_t row, int k) {
+    uint32_t x = (row + static_cast<uint32_t>(k >> 1)) ^ key.s0;
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x += key.s1;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ uint64_t attn_drop_hash(unsigned long long seed, int bh, int S, int q, int k) {
-    const uint64_t half = static_cast<uint64_t>((S + 1) >> 1);
-    const uint64_t blk = (static_cast<uint64_t>(bh) * half + static_cast<uint64_t>(q >> 1)) * half + static_cast<uint64_t>(k >> 1);
-    return attn_mix64(seed + 0x9e3779b97f4a7c15ull * (blk + 1));
-}
-__device__ __forceinline__ bool attn_drop_keep(uint64_t hsh, int q, int k, uint32_t thr) {
-    return ((static_cast<uint32_t>(hsh >> (16 * (((q & 1) << 1) | (k & 1))))) & 0xffffu) >= thr;
+__device__ __forceinline__ bool attn_drop_keep(uint32_t hsh, int k, uint32_t thr) {
+    return ((hsh >> (16 * (k & 1))) & 0xffffu) >= thr;
 }
 
 // 64-column box c of head h, rows [row, row + box_rows): 2-D map {row width, tokens} or, for padded head dims, 3-D map
@@ -255,6 +266,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int q_idx = q0 + r;
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         const float sl2 = p.scale * LOG2E_F;
+        const DropKey drop_key = attn_drop_key(p.drop_seed);
+        const uint32_t drop_row = attn_drop_row(b * p.H + h, p.S, q_idx);
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < n_blocks; ++j) {
             mbar_wait(&s_full[j & 1], (j >> 1) & 1);
@@ -318,9 +331,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                     for (int i2 = 0; i2 < 4; ++i2) {
                         const int kv = kv0 + cc * 8 + 2 * i2;
-                        const uint64_t hsh = attn_drop_hash(p.drop_seed, b * p.H + h, p.S, q_idx, kv);
-                        e[2 * i2] = attn_drop_keep(hsh, q_idx, kv, p.drop_thr) ? e[2 * i2] * p.drop_scale : 0.f;
-                        e[2 * i2 + 1] = attn_drop_keep(hsh, q_idx, kv + 1, p.drop_thr) ? e[2 * i2 + 1] * p.drop_scale : 0.f;
+                        const uint32_t hsh = attn_drop_hash(drop_key, drop_row, kv);
+                        e[2 * i2] = attn_drop_keep(hsh, kv, p.drop_thr) ? e[2 * i2] * p.drop_scale : 0.f;
+                        e[2 * i2 + 1] = attn_drop_keep(hsh, kv + 1, p.drop_thr) ? e[2 * i2 + 1] * p.drop_scale : 0.f;
                     }
                 }
                 st_operand_chunk(sP + (j & 1) * L::P_BYTES, r, cc, make_uint4(f2_to_bf2(e[0], e[1]), f2_to_bf2(e[2], e[3]), f2_to_bf2(e[4], e[5]), f2_to_bf2(e[6], e[7])));
@@ -1022,30 +1035,42 @@ attn_fwd256s_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // backward
 // =================================================================================================================
 // delta[b,h,s] = sum_d dO * O ; one warp per (token, head)
+// LPR lanes per (token, head) row: 8 for head_dim <= 64, 16 up to 128, 32 beyond — a warp covers 32 / LPR consecutive rows, so every
+// lane loads 16 bytes per operand whatever the head size (round 1 gave a whole warp to each row: at head_dim 64 only 8 of 32 lanes
+// worked and the pass ran at 1.3 TB/s, 2.6 % of the Pythia-410m micro-batch).
+template <int LPR>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const elem_t* __restrict__ o, const elem_t* __restrict__ d_o, float* __restrict__ delta,
                   int B, int S, int H, int D, int64_t row_stride, int64_t head_stride) {
     pdl_prologue();
+    constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, rsel = lane / LPR;
     const int64_t total = static_cast<int64_t>(B) * S * H;
-    for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); w < total;
-         w += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
-        const int hh = static_cast<int>(w % H);
-        const int64_t t = w / H;
+    const int64_t n_groups = (total + RPW - 1) / RPW;
+    for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups;
+         g += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
+        const int64_t w = g * RPW + rsel;
+        const bool ok = w < total;
+        const int hh = ok ? static_cast<int>(w % H) : 0;
+        const int64_t t = ok ? w / H : 0;
         const elem_t* op = o + t * row_stride + hh * head_stride;
         const elem_t* dp = d_o + t * row_stride + hh * head_stride;
         float s = 0.f;
-        for (int c = lane * 8; c < D; c += 256) {
-            const uint4 a = ld_nc_v4(op + c), g = ld_nc_v4(dp + c);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+        if (ok) {
+            for (int c = sub * 8; c < D; c += LPR * 8) {
+                const uint4 a = ld_nc_v4(op + c), g4 = ld_nc_v4(dp + c);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 x = bf2_to_f2(aw[i]), y = bf2_to_f2(gw[i]);
-                s += x.x * y.x + x.y * y.y;
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = bf2_to_f2(aw[i]), y = bf2_to_f2(gw[i]);
+                    s += x.x * y.x + x.y * y.y;
+                }
             }
         }
-        s = warp_sum(s);
-        if (lane == 0) {
+#pragma unroll
+        for (int off = LPR / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (ok && sub == 0) {
             const int bb = static_cast<int>(t / S), ss = static_cast<int>(t % S);
             delta[(static_cast<size_t>(bb) * H + hh) * S + ss] = s;
         }
@@ -1343,16 +1368,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmR1, const __grid_constant_
                     const float pe3 = ex2(fmaf(__uint_as_float(sv[4 * q4 + 3]), sl2, l4.w));
                     float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;  // dropout mask / keep probability
                     if (DROP) {
-                        const int cq = ch + 4 * q4;  // streamed index of the first of the 4 elements
+                        const int cq = ch + 4 * q4;  // streamed index of the first of the 4 elements (a multiple of 4)
                         const int bh = b * p.H + h;
+                        const DropKey dkey = attn_drop_key(p.drop_seed);
                         // (query, key) of element e: dQ pass (r_idx, cq + e); dK/dV pass (cq + e, r_idx)
-                        const uint64_t ha = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq);
-                        const uint64_t hb = DKV ? attn_drop_hash(p.drop_seed, bh, p.S, cq + 2, r_idx) : attn_drop_hash(p.drop_seed, bh, p.S, r_idx, cq + 2);
-                        auto keep = [&](uint64_t hsh, int e) { return DKV ? attn_drop_keep(hsh, cq + e, r_idx, p.drop_thr) : attn_drop_keep(hsh, r_idx, cq + e, p.drop_thr); };
-                        m0 = keep(ha, 0) ? p.drop_scale : 0.f;
-                        m1 = keep(ha, 1) ? p.drop_scale : 0.f;
-                        m2 = keep(hb, 2) ? p.drop_scale : 0.f;
-                        m3 = keep(hb, 3) ? p.drop_scale : 0.f;
+                        if (!DKV) {  // one hash per key pair of this thread's query row
+                            const uint32_t row = attn_drop_row(bh, p.S, r_idx);
+                            const uint32_t ha = attn_drop_hash(dkey, row, cq), hb = attn_drop_hash(dkey, row, cq + 2);
+                            m0 = attn_drop_keep(ha, cq, p.drop_thr) ? p.drop_scale : 0.f;
+                            m1 = attn_drop_keep(ha, cq + 1, p.drop_thr) ? p.drop_scale : 0.f;
+                            m2 = attn_drop_keep(hb, cq + 2, p.drop_thr) ? p.drop_scale : 0.f;
+                            m3 = attn_drop_keep(hb, cq + 3, p.drop_thr) ? p.drop_scale : 0.f;
+                        } else {  // this thread's key against four consecutive query rows: one hash each
+                            const uint32_t row0 = attn_drop_row(bh, p.S, cq), step = static_cast<uint32_t>((p.S + 1) >> 1);
+                            m0 = attn_drop_keep(attn_drop_hash(dkey, row0, r_idx), r_idx, p.drop_thr) ? p.drop_scale : 0.f;
+                            m1 = attn_drop_keep(attn_drop_hash(dkey, row0 + step, r_idx), r_idx, p.drop_thr) ? p.drop_scale : 0.f;
+                            m2 = attn_drop_keep(attn_drop_hash(dkey, row0 + 2 * step, r_idx), r_idx, p.drop_thr) ? p.drop_scale : 0.f;
+                            m3 = attn_drop_keep(attn_drop_hash(dkey, row0 + 3 * step, r_idx), r_idx, p.drop_thr) ? p.drop_scale : 0.f;
+                        }
                     }
                     // P^T operand of dV carries the mask; dS = P * (mask * dP - delta)
                     pk[2 * q4] = f2_to_bf2(pe0 * m0, pe1 * m1);
@@ -2068,12 +2101,18 @@ extern "C" int b200_attention_bwd(const b200_attn_args* a, b200_stream_t stream)
     static const bool old_dq = getenv("B200_ATTN_OLD_DQ") != nullptr;  // perf triage only
     const bool score_path = a->D == 256 && a->p_scratch != nullptr && a->ds_scratch != nullptr && a->S % 256 == 0 && a->dropout_p == 0.f;
     {
-        const int64_t total_warps = static_cast<int64_t>(a->B) * a->S * a->H;
+        const int lpr = a->D <= 64 ? 8 : (a->D <= 128 ? 16 : 32);
+        const int64_t total_warps = (static_cast<int64_t>(a->B) * a->S * a->H + (32 / lpr) - 1) / (32 / lpr);
         int64_t blocks = (total_warps + 7) / 8;
         const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
         if (blocks > cap) blocks = cap;
-        launch_k(attn_delta_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, static_cast<const elem_t*>(a->o), static_cast<const elem_t*>(a->d_o),
-                                                                    a->delta, a->B, a->S, a->H, a->D, a->o_row_stride, a->o_head_stride);
+        auto go = [&](auto kern) {
+            launch_k(kern, dim3(static_cast<int>(blocks)), dim3(256), 0, st, static_cast<const elem_t*>(a->o), static_cast<const elem_t*>(a->d_o),
+                     a->delta, a->B, a->S, a->H, a->D, a->o_row_stride, a->o_head_stride);
+        };
+        if (lpr == 8) go(attn_delta_kernel<8>);
+        else if (lpr == 16) go(attn_delta_kernel<16>);
+        else go(attn_delta_kernel<32>);
         if ((rc = check_launch("attention_delta"))) return rc;
     }
     switch (a->D) {

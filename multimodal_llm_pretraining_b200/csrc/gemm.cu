@@ -59,7 +59,22 @@ struct GemmParams {
     // DRAM once); group_m = g > 0 -> groups of g m-tiles, m fastest inside a group (the g A panels stay L2-resident while B streams)
     int group_m;
     unsigned long long hint_a, hint_b;  // L2 eviction-priority hints of the operand loads (common.cuh)
+    // fused nn.Dropout on the value BEFORE the residual is added (RoBERTa: LN(dropout(W x + b) + residual)): the same counter-based
+    // mask as elementwise.cu: dropout_kernel over the flat element index row * ldc + col, so the stand-alone kernel applied to the
+    // gradient with the same seed is its backward. drop_thr = 0: off.
+    uint32_t drop_thr;
+    float drop_scale;
+    unsigned long long drop_seed;
 };
+
+__device__ __forceinline__ uint64_t gemm_mix64(uint64_t x) {  // splitmix64 finaliser (== elementwise.cu: mix64)
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int GROUP, int& tm, int& tn) {
     if (GROUP <= 0) {  // n fastest
@@ -124,6 +139,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 const float2 h = bf2_to_f2(hw[j]);
                 x[2 * j] *= gelu_erf_grad(h.x);
                 x[2 * j + 1] *= gelu_erf_grad(h.y);
+            }
+        }
+        if (EPI == 0 && SIDE && p.drop_thr) {
+            // 8 consecutive elements = vector i of the flat [M, ldc] output: lanes of two 64-bit hashes (see dropout_kernel)
+            const uint64_t vi = (static_cast<uint64_t>(row) * static_cast<uint64_t>(p.ldc) + static_cast<uint64_t>(col)) >> 3;
+            const uint64_t h0 = gemm_mix64(p.drop_seed + 0x9e3779b97f4a7c15ull * (2 * vi + 1));
+            const uint64_t h1 = gemm_mix64(p.drop_seed + 0x9e3779b97f4a7c15ull * (2 * vi + 2));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t hh = j < 2 ? h0 : h1;
+                const uint32_t ra = static_cast<uint32_t>(hh >> (32 * (j & 1))) & 0xffffu, rb = static_cast<uint32_t>(hh >> (32 * (j & 1) + 16)) & 0xffffu;
+                x[2 * j] = ra >= p.drop_thr ? x[2 * j] * p.drop_scale : 0.f;
+                x[2 * j + 1] = rb >= p.drop_thr ? x[2 * j + 1] * p.drop_scale : 0.f;
             }
         }
         if (p.residual) {
@@ -665,6 +693,9 @@ static void fill_params(const b200_gemm_args* a, GemmParams& p) {
     p.split_k = 1;
     p.group_m = 8;
     p.hint_a = L2_EVICT_NORMAL, p.hint_b = L2_EVICT_NORMAL;
+    p.drop_thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr);
+    p.drop_seed = a->dropout_seed;
 }
 
 // Raster and L2 policy of a plain (non-batched) problem. A wave = one tile per CTA (pair), all streaming K in lockstep, so what
@@ -738,6 +769,9 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     p.debug = dbg;
     p.tma_store = (!a->c_fp32 && !a->accumulate && !(dbg & 64)) ? 1 : 0;
     B200_REQUIRE(!a->aux_out || a->gelu, "gemm: aux_out is the pre-GELU output and needs gelu=1");
+    B200_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "gemm: dropout_p must be in [0, 1)");
+    B200_REQUIRE(a->dropout_p == 0.f || (a->residual && !a->gelu && !a->dgelu_in && !a->c_fp32 && !a->accumulate && a->ldc % 8 == 0),
+                 "gemm: the fused dropout is built for the bias + dropout + residual epilogue with a 16-bit output");
     cudaStream_t st = as_stream(stream);
     // CTA pairs on 256 x 256 tiles when the problem fills them; 128 x 256 / 128 x 128 single-CTA tiles otherwise
     if (a->N > 128 && a->M > 128 && force_cg != 1) {

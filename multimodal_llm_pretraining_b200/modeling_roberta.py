@@ -262,18 +262,14 @@ class B200RobertaForMaskedLM(_FlatModule):
         o, lse = K.attention_fwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=False, scale=hd ** -0.5, dropout_p=pa, dropout_seed=self._seed(4 * i + 3))
         o2 = o.view(B * S, h)
         wo, bo = self._w(f"{p}.attention.output.dense.weight"), self._p(f"{p}.attention.output.dense.bias")
-        if drop:
-            s1 = self._drop(K.gemm(o2, wo, bias=bo), x, 4 * i + 1)
-        else:
-            s1 = K.gemm(o2, wo, bias=bo, residual=x)
+        # hidden dropout fused into the GEMM epilogue: dropout(W o + b) + x in one pass (same mask as K.dropout(seed), which backward
+        # applies to the gradient)
+        s1 = K.gemm(o2, wo, bias=bo, residual=x, dropout_p=self.p_hidden if drop else 0.0, dropout_seed=self._seed(4 * i + 1))
         x1, _, mean1, rstd1 = K.layernorm_fwd(s1, self._p(f"{p}.attention.output.LayerNorm.weight"), self._p(f"{p}.attention.output.LayerNorm.bias"), self.eps)
         h1 = torch.empty(B * S, self.inter, dtype=x.dtype, device=x.device)
         g = K.gemm(x1, self._w(f"{p}.intermediate.dense.weight"), bias=self._p(f"{p}.intermediate.dense.bias"), gelu=True, aux_out=h1)
         w2, b2 = self._w(f"{p}.output.dense.weight"), self._p(f"{p}.output.dense.bias")
-        if drop:
-            s2 = self._drop(K.gemm(g, w2, bias=b2), x1, 4 * i + 2)
-        else:
-            s2 = K.gemm(g, w2, bias=b2, residual=x1)
+        s2 = K.gemm(g, w2, bias=b2, residual=x1, dropout_p=self.p_hidden if drop else 0.0, dropout_seed=self._seed(4 * i + 2))
         x2, _, mean2, rstd2 = K.layernorm_fwd(s2, self._p(f"{p}.output.LayerNorm.weight"), self._p(f"{p}.output.LayerNorm.bias"), self.eps)
         return x2, (x, qkv, o, lse, s1, mean1, rstd1, x1, h1, g, s2, mean2, rstd2)
 

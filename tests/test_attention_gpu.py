@@ -132,26 +132,29 @@ def test_attention_bwd_d256_scratch_paths_agree_and_ignore_stale_scratch(dev, us
 
 
 def _drop_keep_mask(seed, B, H, S, p):
-    """Host restatement of the kernels' counter-based mask (attention.cu attn_drop_hash / attn_drop_keep): one splitmix64
-    hash per 2 x 2 block of each head's [S, S] score matrix, 16-bit lane (q & 1) * 2 + (k & 1) compared with round(p * 65536)."""
+    """Host restatement of the kernels' counter-based mask (attention.cu attn_drop_key / attn_drop_row / attn_drop_hash /
+    attn_drop_keep): one 32-bit hash per (query, key pair), 16-bit lane k & 1 compared with round(p * 65536)."""
     import numpy as np
 
-    thr = np.uint64(int(p * 65536.0 + 0.5))
+    thr = np.uint32(int(p * 65536.0 + 0.5))
+    M = np.uint64(0xFFFFFFFF)
+    u = lambda v: np.uint64(v) & M  # noqa: E731 - 32-bit wrap-around arithmetic carried in uint64
+    s0 = u(u(seed & 0xFFFFFFFF) * np.uint64(0x9E3779B1) + np.uint64(0x85EBCA6B))
+    s1 = u((seed >> 32) & 0xFFFFFFFF) ^ np.uint64(0xC2B2AE35)
     half = np.uint64((S + 1) // 2)
     bh = np.arange(B * H, dtype=np.uint64)[:, None, None]
     q = np.arange(S, dtype=np.uint64)[None, :, None]
     k = np.arange(S, dtype=np.uint64)[None, None, :]
-    with np.errstate(over="ignore"):
-        blk = (bh * half + (q >> np.uint64(1))) * half + (k >> np.uint64(1))
-        x = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (blk + np.uint64(1))
-        x ^= x >> np.uint64(30)
-        x *= np.uint64(0xBF58476D1CE4E5B9)
-        x ^= x >> np.uint64(27)
-        x *= np.uint64(0x94D049BB133111EB)
-        x ^= x >> np.uint64(31)
-        lane = ((q & np.uint64(1)) << np.uint64(1)) | (k & np.uint64(1))
-        bits = (x >> (np.uint64(16) * lane)) & np.uint64(0xFFFF)
-    keep = bits >= thr
+    row = ((bh * np.uint64(S) + q) & M) * half & M
+    x = ((row + (k >> np.uint64(1))) & M) ^ s0
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15)
+    x = (x + s1) & M
+    x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    bits = (x >> (np.uint64(16) * (k & np.uint64(1)))) & np.uint64(0xFFFF)
+    keep = bits >= np.uint64(thr)
     return torch.from_numpy(keep.reshape(B, H, S, S)), 65536.0 / (65536.0 - float(thr))
 
 

@@ -217,3 +217,27 @@ def test_activation_checkpointing_reproduces_gradients_with_dropout(gold, dev):
         grads.append((loss.item(), m.flat.grad.clone()))
     assert grads[0][0] == grads[1][0]
     assert rel(grads[1][1], grads[0][1]) <= 1e-5
+
+
+def test_gemm_fused_dropout_equals_standalone_dropout_kernel(dev):
+    """dropout fused into the bias + residual GEMM epilogue must draw the mask of K.dropout(seed) (its backward is that kernel applied to
+    the gradient): same kept set; kept values differ only by the bf16 rounding the unfused path adds between the GEMM and the dropout."""
+    for M, N, Kd in [(512, 1024, 256), (200, 136, 64), (4096, 1024, 1024)]:
+        g = torch.Generator(device="cpu").manual_seed(M)
+        A = torch.randn(M, Kd, generator=g).to(dev).to(torch.bfloat16)
+        W = (torch.randn(N, Kd, generator=g) * 0.05).to(dev).to(torch.bfloat16)
+        b = torch.randn(N, generator=g).to(dev)
+        res = torch.randn(M, N, generator=g).to(dev).to(torch.bfloat16)
+        z = K.gemm(A, W, bias=b)
+        want = K.dropout(z, 0.1, seed=77, residual=res)
+        got = K.gemm(A, W, bias=b, residual=res, dropout_p=0.1, dropout_seed=77)
+        dropped_ref = (want == res)
+        dropped = (got == res)
+        assert (dropped_ref != dropped).float().mean().item() < 1e-4  # coincidences where z rounds to 0 only
+        frac = dropped.float().mean().item()
+        assert abs(frac - 0.1) < 0.01, frac
+        assert rel(got, want) <= 5e-3, rel(got, want)
+        # backward of the fused op = the stand-alone kernel on the gradient with the same seed: zero exactly where the forward dropped
+        gr = torch.ones(M, N, device=dev, dtype=torch.bfloat16)
+        gmask = K.dropout(gr, 0.1, seed=77)
+        assert ((gmask == 0) != dropped).float().mean().item() < 1e-4
