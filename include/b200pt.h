@@ -148,6 +148,10 @@ typedef struct b200_gemm_args {
      * dropout_p = 0 is off. */
     float dropout_p;
     uint64_t dropout_seed;
+    /* dGELU dgrad only (dgelu_in != NULL), nullable fp32 [N]: colsum_out[n] += sum_m C[m, n] (of the fp32 values before the
+     * 16-bit rounding) — the bias gradient of the Linear in front of the GELU (mlp.dense_h_to_4h.bias, HF:modeling_gpt_neox.py:
+     * 41-47), reduced in the epilogue instead of a separate b200_colsum_bf16 pass over the [M, N] gradient. */
+    float* colsum_out;
 } b200_gemm_args;
 int b200_gemm_bf16(const b200_gemm_args* args, b200_stream_t stream);
 

@@ -65,6 +65,9 @@ struct GemmParams {
     uint32_t drop_thr;
     float drop_scale;
     unsigned long long drop_seed;
+    // dGELU dgrad only: colsum_out[n] += sum_m C[m, n] — the bias gradient of the Linear in front of the GELU, reduced in the
+    // epilogue (its warps wait for the tensor pipe most of the time) instead of a separate pass over the 0.5 GB dh1 tensor
+    float* colsum_out;
 };
 
 __device__ __forceinline__ uint64_t gemm_mix64(uint64_t x) {  // splitmix64 finaliser (== elementwise.cu: mix64)
@@ -139,6 +142,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 const float2 h = bf2_to_f2(hw[j]);
                 x[2 * j] *= gelu_erf_grad(h.x);
                 x[2 * j + 1] *= gelu_erf_grad(h.y);
+            }
+            if (p.colsum_out) {  // uniform; rows beyond M hold exact zeros (zero-filled A and side tiles)
+                float cs[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float t = x[j];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    cs[j] = t;
+                }
+                if ((threadIdx.x & 31) == 0) {
+                    red_add_v4(p.colsum_out + col, cs[0], cs[1], cs[2], cs[3]);
+                    red_add_v4(p.colsum_out + col + 4, cs[4], cs[5], cs[6], cs[7]);
+                }
             }
         }
         if (EPI == 0 && SIDE && p.drop_thr) {
@@ -696,6 +713,7 @@ static void fill_params(const b200_gemm_args* a, GemmParams& p) {
     p.drop_thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     p.drop_scale = 65536.0f / static_cast<float>(65536u - p.drop_thr);
     p.drop_seed = a->dropout_seed;
+    p.colsum_out = a->colsum_out;
 }
 
 // Raster and L2 policy of a plain (non-batched) problem. A wave = one tile per CTA (pair), all streaming K in lockstep, so what
@@ -770,6 +788,7 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     p.tma_store = (!a->c_fp32 && !a->accumulate && !(dbg & 64)) ? 1 : 0;
     B200_REQUIRE(!a->aux_out || a->gelu, "gemm: aux_out is the pre-GELU output and needs gelu=1");
     B200_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "gemm: dropout_p must be in [0, 1)");
+    B200_REQUIRE(!a->colsum_out || (a->dgelu_in && aligned16(a->colsum_out)), "gemm: colsum_out is built for the dGELU dgrad epilogue (needs dgelu_in) and must be 16B aligned");
     B200_REQUIRE(a->dropout_p == 0.f || (a->residual && !a->gelu && !a->dgelu_in && !a->c_fp32 && !a->accumulate && a->ldc % 8 == 0),
                  "gemm: the fused dropout is built for the bias + dropout + residual epilogue with a 16-bit output");
     cudaStream_t st = as_stream(stream);

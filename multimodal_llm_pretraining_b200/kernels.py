@@ -202,7 +202,7 @@ def colsum_(x, out, out2=None, scale=None):
 
 # ----------------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=None, accumulate=False, bias=None, residual=None,
-         gelu=False, alpha=None, aux_out=None, dgelu_in=None, dropout_p: float = 0.0, dropout_seed: int = 0):
+         gelu=False, alpha=None, aux_out=None, dgelu_in=None, dropout_p: float = 0.0, dropout_seed: int = 0, colsum_out=None):
     """C[M,N] = epi(alpha * A·Bᵀ).  A is [M,K] (a_mn=False) or [K,M] (a_mn=True); B is [N,K] or [K,N] (b_mn=True).
     dropout_p > 0 (needs residual): C = dropout(alpha * A·Bᵀ + bias) + residual with K.dropout's mask of (dropout_seed, element)."""
     _req(A.dtype in HALF and B.dtype == A.dtype and A.dim() == 2 and B.dim() == 2, "gemm: A,B must be 2-D bf16 (or both fp16)")
@@ -246,6 +246,10 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=None, accumulate=F
     if aux_out is not None:
         _req(aux_out.dtype == E and aux_out.shape == (M, N) and aux_out.stride(0) == out.stride(0) and out.dtype == E, "gemm: aux_out must match a 16-bit out")
         a.aux_out = ptr(aux_out)
+    if colsum_out is not None:
+        _req(dgelu_in is not None and colsum_out.dtype == F32 and colsum_out.numel() == N and colsum_out.is_contiguous(),
+             "gemm: colsum_out (fp32 [N], accumulated) rides in the dGELU dgrad epilogue only")
+        a.colsum_out = ptr(colsum_out)
     if dropout_p > 0.0:
         _req(residual is not None and out.is_contiguous(), "gemm: fused dropout needs a residual and a contiguous output")
         a.dropout_p, a.dropout_seed = float(dropout_p), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF

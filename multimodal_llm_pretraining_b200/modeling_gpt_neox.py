@@ -14,6 +14,7 @@ Numerics: fp32 master parameters, bf16 compute copies and activations, fp32 accu
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -23,6 +24,11 @@ from . import kernels as K
 from .flat import FlatParams
 
 BF16 = torch.bfloat16
+# bias gradient of dense_h_to_4h from the dGELU dgrad epilogue (b200_gemm_args.colsum_out) instead of a column-sum pass over dh1.
+# Built, parity-tested (tests/test_kernels_gpu.py::test_gemm_epilogues) and measured on the Pythia-1b step: 183.8 / 184.2 k tokens/s
+# fused against 185.0 / 184.7 k separate (alternating, one box): the 40 shuffles + 2 vector reductions per 8 columns cost the
+# epilogue more than the 90 us pass they replace (in-step GEMM rate 1302 -> 1277 TFLOP/s). Off unless B200_FUSED_BIAS_GRAD=1.
+FUSED_BIAS_GRAD = bool(os.environ.get("B200_FUSED_BIAS_GRAD"))
 
 
 class ModelOutput(dict):
@@ -300,9 +306,13 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         K.gemm(dy, g, a_mn=True, b_mn=True, out=self._g(f"{p}.mlp.dense_4h_to_h.weight"), accumulate=True)
         # both output biases of the parallel-residual block see the same upstream gradient: one column-sum pass, two accumulators
         K.colsum_(dy, self._g(f"{p}.mlp.dense_4h_to_h.bias"), out2=self._g(f"{p}.attention.dense.bias"))
-        dh1 = K.gemm(dy, self._w(f"{p}.mlp.dense_4h_to_h.weight"), b_mn=True, dgelu_in=h1)
+        # dgrad through W2 with gelu'(h1) and the bias gradient of dense_h_to_4h (column sums of dh1) in the same epilogue
+        if FUSED_BIAS_GRAD:
+            dh1 = K.gemm(dy, self._w(f"{p}.mlp.dense_4h_to_h.weight"), b_mn=True, dgelu_in=h1, colsum_out=self._g(f"{p}.mlp.dense_h_to_4h.bias"))
+        else:
+            dh1 = K.gemm(dy, self._w(f"{p}.mlp.dense_4h_to_h.weight"), b_mn=True, dgelu_in=h1)
+            K.colsum_(dh1, self._g(f"{p}.mlp.dense_h_to_4h.bias"))
         K.gemm(dh1, a2, a_mn=True, b_mn=True, out=self._g(f"{p}.mlp.dense_h_to_4h.weight"), accumulate=True)
-        K.colsum_(dh1, self._g(f"{p}.mlp.dense_h_to_4h.bias"))
         da2 = K.gemm(dh1, self._w(f"{p}.mlp.dense_h_to_4h.weight"), b_mn=True)
         del dh1
         # --- attention branch

@@ -195,6 +195,9 @@ def test_gemm_epilogues(dev, M, N, Kd):
     torch.nn.functional.gelu(hf).backward(base)
     Wt = W.t().contiguous()  # dgrad layout: B stored [K, N]
     check(K.gemm(A, Wt, b_mn=True, dgelu_in=h), hf.grad, 5e-3, "fused dgelu")
+    cs = torch.full((N,), 0.25, device=dev)  # accumulate semantics: starts non-zero
+    check(K.gemm(A, Wt, b_mn=True, dgelu_in=h, colsum_out=cs), hf.grad, 5e-3, "fused dgelu + column sums (output)")
+    check(cs - 0.25, hf.grad.sum(0), 2e-3, "column sums of the dgelu dgrad (bias gradient) from the epilogue")
     acc = torch.randn(M, N, generator=g).to(dev)
     want = acc + base
     K.gemm(A, W, out=acc, accumulate=True)
