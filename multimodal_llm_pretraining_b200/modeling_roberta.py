@@ -284,9 +284,13 @@ class B200RobertaForMaskedLM(_FlatModule):
         dz = K.dropout(ds2, self.p_hidden, self._seed(4 * i + 2)) if drop else ds2
         K.gemm(dz, g, a_mn=True, b_mn=True, out=self._g(f"{p}.output.dense.weight"), accumulate=True)
         K.colsum_(dz, self._g(f"{p}.output.dense.bias"))
-        dh1 = K.gemm(dz, self._w(f"{p}.output.dense.weight"), b_mn=True, dgelu_in=h1)
+        from .modeling_gpt_neox import FUSED_BIAS_GRAD  # opt-in, see there
+
+        dh1 = K.gemm(dz, self._w(f"{p}.output.dense.weight"), b_mn=True, dgelu_in=h1,
+                     colsum_out=self._g(f"{p}.intermediate.dense.bias") if FUSED_BIAS_GRAD else None)
         K.gemm(dh1, x1, a_mn=True, b_mn=True, out=self._g(f"{p}.intermediate.dense.weight"), accumulate=True)
-        K.colsum_(dh1, self._g(f"{p}.intermediate.dense.bias"))
+        if not FUSED_BIAS_GRAD:
+            K.colsum_(dh1, self._g(f"{p}.intermediate.dense.bias"))
         dx1 = K.gemm(dh1, self._w(f"{p}.intermediate.dense.weight"), b_mn=True, residual=ds2)  # + residual branch of s2
         # x1 = LN1(s1), s1 = drop(y) + x, y = Wo ctx + bo
         ds1 = K.layernorm_bwd(s1, mean1, rstd1, self._p(f"{p}.attention.output.LayerNorm.weight"), dx1,
