@@ -10,6 +10,7 @@ for RoBERTa (src/models/pythia.py:33-41, src/models/roberta.py:29-30; DeepSpeed 
  * an fp16 model step against live fp32 HF (loss, gradients after unscaling) and a 410m-shaped layer.
 """
 import math
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -335,9 +336,12 @@ def _run_py(code: str):
     return subprocess.run([sys.executable, "-c", f"import sys; sys.path.insert(0, {str(ROOT)!r})\n" + code], capture_output=True, text=True, timeout=300)
 
 
+@pytest.mark.skipif(not os.environ.get("B200_RUN_TRAP_TESTS"), reason="raises a deliberate device-side trap (an Xid on the host): opt-in with "
+                    "B200_RUN_TRAP_TESTS=1; ran green on B200 twice this round (gpurun_out/r02_gputest1.log, r02_gputest4.log)")
 def test_out_of_range_label_and_token_id_trap_like_torch():
     """A label outside [0, V) that is not ignore_index, or a token id outside the table, would read out of bounds: both trap
-    with a message (torch raises a device-side assert). Own processes: a trap poisons the CUDA context."""
+    with a message (torch raises a device-side assert). Own processes: a trap poisons the CUDA context. Opt-in: a trapped kernel is
+    logged by the driver as a GPU exception, which a shared test box may treat as a fault of the lease."""
     r = _run_py("""
 import torch
 from multimodal_llm_pretraining_b200 import kernels as K
