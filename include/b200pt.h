@@ -215,11 +215,14 @@ typedef struct b200_adam_group {
 int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
                    const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group,
                    const int64_t* chunk_state, int n_chunks, const b200_adam_group* groups, int n_groups,
-                   const float* grad_scale_dev, int zero_grad, const int* skip_flag_dev, int g_packed, b200_stream_t stream);
+                   const float* grad_scale_dev, int zero_grad, const int* skip_flag_dev, int g_packed, int p_packed,
+                   b200_stream_t stream);
 /* skip_flag_dev (nullable device int): when *skip_flag_dev != 0 the step leaves p, m, v and the shadow untouched (an fp16
  * overflow step, torch.amp.GradScaler.step semantics); g is still cleared when zero_grad != 0.
  * g_packed != 0: g is a packed shard buffer indexed like m / v (chunk_state[c] + i) instead of the full flat gradient buffer —
- * ZeRO-2 (src/train.py:172-181), where a rank only holds the reduced gradients of the slices it owns. */
+ * ZeRO-2 (src/train.py:172-181), where a rank only holds the reduced gradients of the slices it owns.
+ * p_packed != 0: p likewise is a packed shard buffer (the fp32 master exists only on the owning rank, 4 B/param/W — DeepSpeed's
+ * ZeRO partition of the fp32 weights); p_bf16 stays the full replicated 16-bit copy, indexed by absolute offset. */
 
 /* out[0] += sum(x[i]^2), DETERMINISTIC (fixed per-block partials into `workspace`, then a fixed-order final sum; no atomics):
  * replicas holding identical gradients get bit-identical norms. workspace: b200_sumsq_workspace_bytes() bytes. */

@@ -89,7 +89,7 @@ SIGNATURES = {
     "b200_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "b200_attention_fwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
     "b200_attention_bwd": (c_int, [C.POINTER(AttnArgs), c_void_p]),
-    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "b200_adam_step": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(AdamGroup), c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b200_sumsq_workspace_bytes": (c_size_t, []),
     "b200_sumsq": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_sumsq_chunks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -32,7 +32,7 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             elem_t* __restrict__ p16, int64_t state_base, const int64_t* __restrict__ chunk_start,
             const int32_t* __restrict__ chunk_len, const int32_t* __restrict__ chunk_group,
             const int64_t* __restrict__ chunk_state, const AdamGroups groups, const float* __restrict__ grad_scale,
-            int zero_grad, const int* __restrict__ skip_flag, int g_packed) {
+            int zero_grad, const int* __restrict__ skip_flag, int g_packed, int p_packed) {
     pdl_prologue();
     const int64_t start = chunk_start[blockIdx.x];
     const int len = chunk_len[blockIdx.x];
@@ -47,7 +47,8 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     }
     const b200_adam_group h = groups.g[chunk_group[blockIdx.x]];
     const float gs = grad_scale ? *grad_scale : 1.0f;
-    float* pp = p + start;
+    // p_packed: the fp32 master exists only for the slices this rank owns, packed like the moments (true ZeRO: 4 B/param/W)
+    float* pp = p + (p_packed ? soff : start);
     float* mp = m + soff;
     float* vp = v + soff;
     const bool vec_ok = ((start & 3) == 0) && ((soff & 3) == 0);
@@ -193,13 +194,13 @@ using namespace b200;
 extern "C" int b200_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, int64_t state_base,
                               const int64_t* chunk_start, const int32_t* chunk_len, const int32_t* chunk_group,
                               const int64_t* chunk_state, int n_chunks, const b200_adam_group* groups, int n_groups,
-                              const float* grad_scale_dev, int zero_grad, const int* skip_flag_dev, int g_packed, b200_stream_t stream) {
+                              const float* grad_scale_dev, int zero_grad, const int* skip_flag_dev, int g_packed, int p_packed, b200_stream_t stream) {
     B200_REQUIRE(n_groups > 0 && n_groups <= B200_ADAM_MAX_GROUPS, "adam_step: n_groups %d out of range", n_groups);
     if (n_chunks == 0) return 0;
     AdamGroups gs;
     for (int i = 0; i < n_groups; ++i) gs.g[i] = groups[i];
     launch_k(adam_kernel, dim3(n_chunks), dim3(256), 0, as_stream(stream), p, g, m, v, static_cast<elem_t*>(p_bf16), state_base,
-                                                         chunk_start, chunk_len, chunk_group, chunk_state, gs, grad_scale_dev, zero_grad, skip_flag_dev, g_packed);
+                                                         chunk_start, chunk_len, chunk_group, chunk_state, gs, grad_scale_dev, zero_grad, skip_flag_dev, g_packed, p_packed);
     return check_launch("adam_step");
 }
 extern "C" size_t b200_sumsq_workspace_bytes(void) { return SUMSQ_MAX_BLOCKS * sizeof(float); }

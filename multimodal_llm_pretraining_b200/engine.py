@@ -180,7 +180,8 @@ class TrainEngine:
 
     def __init__(self, model, optimizer, scheduler=None, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
                  strategy: str = "none", group=None, overlap: bool = True, comm_max_ctas: int | None = None,
-                 profile_phases: bool = False, loss_scaler: LossScaler | None = None, overlap_param_gather: bool = True):
+                 profile_phases: bool = False, loss_scaler: LossScaler | None = None, overlap_param_gather: bool = True,
+                 shard_master: bool = False):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.max_grad_norm = max_grad_norm
         self.ga = gradient_accumulation_steps
@@ -202,8 +203,8 @@ class TrainEngine:
             raise ValueError(strategy)
         f = self.flat
         # fp16: a loss scale is mandatory (dlogits / n_valid underflow in half precision without it)
-        if getattr(f, "compute_dtype", torch.bfloat16) == torch.float16 and loss_scaler is None and f.master.is_cuda:
-            loss_scaler = LossScaler(f.master.device, kind="deepspeed" if strategy in ("zero1", "zero2") else "torch")
+        if getattr(f, "compute_dtype", torch.bfloat16) == torch.float16 and loss_scaler is None and f.device.type == "cuda":
+            loss_scaler = LossScaler(f.device, kind="deepspeed" if strategy in ("zero1", "zero2") else "torch")
         self.loss_scaler = loss_scaler
         if loss_scaler is not None:
             model.loss_scale = loss_scaler.scale
@@ -213,7 +214,7 @@ class TrainEngine:
             W, r = dist.get_world_size(group), dist.get_rank(group)
             self.plan = CommPlan(model.comm_buckets(), W, r, group)
             # host-side tests drive the exchange logic with CPU tensors over gloo: no side stream there
-            self.comm_stream = torch.cuda.Stream() if f.master.is_cuda else None
+            self.comm_stream = torch.cuda.Stream() if f.device.type == "cuda" else None
             if comm_max_ctas is None:
                 comm_max_ctas = int(os.environ.get("B200_COMM_MAX_CTAS", "0")) or None
             if comm_max_ctas and overlap and dist.get_backend(group) == "nccl":
@@ -233,6 +234,11 @@ class TrainEngine:
             f.sync_shadow(force=True)
             if strategy == "zero2":
                 self._setup_zero2()
+            self.shard_master = bool(shard_master) and strategy in ("zero1", "zero2")
+            if self.shard_master:
+                self._shard_master()
+        else:
+            self.shard_master = False
 
     # ------------------------------------------------------------------ ZeRO-1/2: replicated fp32 1-D parameters
     def _build_fp32_exchange(self) -> None:
@@ -240,7 +246,7 @@ class TrainEngine:
         parameter) from the fp32 master. Those few elements (13 h per layer) are exchanged in fp32 after each optimizer step:
         every rank contributes the elements it owns to one packed buffer, zeros elsewhere, and a SUM all-reduce fills it in."""
         f = self.flat
-        dev = f.master.device
+        dev = f.device
         idx = []
         for name in f.names:
             if len(f.shapes[name]) < 2:
@@ -251,13 +257,79 @@ class TrainEngine:
 
     def _exchange_fp32_params(self) -> None:
         f = self.flat
+        if f.master is None:  # sharded master: owners contribute from their packed fp32 shard, everyone receives into `small`
+            packed = torch.zeros_like(f.small)
+            packed[self._own_small_pos] = self.optimizer._p32[self._own_packed_idx]
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.plan.group)
+            f.small.copy_(packed)
+            return
         self.plan.exchange_owned(f.master, self._fp32_idx, self._fp32_own)
         f.shadow_version = f.current_version()  # a torch-side write to the master that must NOT trigger a shadow re-cast
+
+    # ------------------------------------------------------------------ ZeRO with a sharded fp32 master (opt-in)
+    def _shard_master(self) -> None:
+        """True ZeRO partition of the fp32 weights (12 B/param/W of optimizer state per rank instead of 4 + 8/W): the optimizer adopts
+        the owned slices as a packed fp32 buffer, the full master is freed, the nn.Parameters become views of the 16-bit copy and the
+        1-D parameters the kernels read in fp32 move to the compact replicated `flat.small`."""
+        f = self.flat
+        p32 = self.optimizer.adopt_master_shard()
+        dev = f.device
+        # flat offset -> packed offset of this rank's owned elements, for the 1-D parameters only
+        own_flat = self._fp32_idx[self._fp32_own]
+        packed_off = torch.empty_like(own_flat)
+        acc = 0
+        for lo, hi in self.plan.owned_ranges():
+            m = (own_flat >= lo) & (own_flat < hi)
+            packed_off[m] = own_flat[m] - lo + acc
+            acc += hi - lo
+        f.drop_master(dict(self.model.named_parameters()))
+        # position inside `small` of every 1-D element (small keeps the order of the flat store, padded per name like it)
+        pos = []
+        for n in f.small_names():
+            k = math.prod(f.alloc_shapes[n])
+            pos.append(torch.arange(f.small_offsets[n], f.small_offsets[n] + k, dtype=torch.int64))
+        small_pos = torch.cat(pos).to(dev) if pos else torch.empty(0, dtype=torch.int64, device=dev)
+        self._own_small_pos = small_pos[self._fp32_own]
+        self._own_packed_idx = packed_off
+        f.master_materializer = self._materialize_master
+        f.master_loader = self._load_full_master
+        assert p32 is self.optimizer._p32
+
+    def _materialize_master(self) -> torch.Tensor:
+        """Collective: a fresh full fp32 parameter vector gathered from the owners' shards (state_dict / checkpoints)."""
+        f = self.flat
+        self.sync_params()
+        full = torch.zeros(f.numel, dtype=torch.float32, device=f.device)
+        off = 0
+        for b, (lo, hi) in zip(self.plan.buckets, self.plan.owned_ranges()):
+            full[lo:hi].copy_(self.optimizer._p32[off:off + hi - lo])
+            off += hi - lo
+            self.plan.all_gather(full, b)
+        return full
+
+    def _load_full_master(self, full: torch.Tensor) -> None:
+        """Inverse: scatter a full fp32 vector (identical on every rank) into the shard, `small` and the 16-bit copy."""
+        f = self.flat
+        self.sync_params()
+        off = 0
+        for lo, hi in self.plan.owned_ranges():
+            self.optimizer._p32[off:off + hi - lo].copy_(full[lo:hi])
+            off += hi - lo
+        for n in f.small_names():
+            k = math.prod(f.alloc_shapes[n])
+            f.small[f.small_offsets[n]:f.small_offsets[n] + k].copy_(full[f.offsets[n]:f.offsets[n] + k])
+        if f.device.type == "cuda":
+            from . import kernels as K
+
+            K.cast_f32_to_bf16(full, f.shadow)
+        else:
+            f.shadow.copy_(full)
+        self._param_events = {}
 
     # ------------------------------------------------------------------ ZeRO-2: transient bucket buffers + shard accumulator
     def _setup_zero2(self) -> None:
         f = self.flat
-        dev = f.master.device
+        dev = f.device
         owned = self.plan.owned_ranges()
         self._gshard = torch.zeros(sum(hi - lo for lo, hi in owned), dtype=torch.float32, device=dev)
         self._gshard_off, acc = {}, 0  # packed exactly like the optimizer's moments: owned ranges back to back
@@ -363,7 +435,7 @@ class TrainEngine:
         from . import kernels as K
 
         f = self.flat
-        sumsq = torch.zeros((), dtype=torch.float32, device=f.master.device)
+        sumsq = torch.zeros((), dtype=torch.float32, device=f.device)
         if self.strategy == "zero2":
             K.sumsq_(self._gshard, sumsq)
             self.plan.all_reduce_sum_scalar(sumsq)
@@ -459,7 +531,7 @@ class TrainEngine:
                     e.record()
                     events[tuple(b)] = e
             self._param_events = events
-        f.master_stale = True  # of the 2-D parameters a rank does not own; nothing on the step path reads those
+        f.master_stale = f.master is not None  # of the 2-D parameters a rank does not own; nothing on the step path reads those
 
     def sync_params(self) -> None:
         """Make the current stream wait for every outstanding parameter gather (before reading the parameters outside the
@@ -539,6 +611,8 @@ class TrainEngine:
         """ZeRO: bring the fp32 master of every slice up to date on every rank (collective; all ranks must call it).
         The owner's fp32 values are authoritative; between optimizer steps only the 16-bit compute copy is replicated."""
         f = self.flat
+        if f.master is None:
+            return  # sharded master: materialised on demand (flat.materialize_master)
         if self.strategy in ("zero1", "zero2") and getattr(f, "master_stale", False):
             self.sync_params()
             for b in self.plan.buckets:

@@ -51,6 +51,68 @@ class FlatParams:
         # `grad_zero_fn()` clears the rank's shard accumulator
         self.grad_router = None
         self.grad_zero_fn = None
+        # Sharded fp32 master (engine.py, shard_master=True): `master` is None — each rank keeps the fp32 values of the slices it owns
+        # inside its optimizer (4 B/param/W) — the nn.Parameters become views of the replicated 16-bit copy (as under DeepSpeed, where
+        # the module is bf16 and the fp32 weights live in the ZeRO partition), and the few fp32 values the kernels read directly
+        # (every 1-D parameter: biases, LayerNorm affine) live in `small`, a compact replicated fp32 buffer.
+        # `master_materializer()` (collective) returns a full fp32 copy on demand, `master_loader(full)` scatters one back.
+        self.small: torch.Tensor | None = None
+        self.small_offsets: dict[str, int] = {}
+        self.master_materializer = None
+        self.master_loader = None
+
+    @property
+    def device(self) -> torch.device:
+        return (self.master if self.master is not None else self.shadow).device
+
+    # ---- fp32 views of the parameters the kernels read in fp32 (1-D: biases, LayerNorm affine)
+    def pview(self, name: str) -> torch.Tensor:
+        if self.master is not None:
+            return self.view(self.master, name)
+        o, s = self.small_offsets[name], self.shapes[name]
+        return self.small[o:o + math.prod(s)].view(s)
+
+    def pview_alloc(self, name: str) -> torch.Tensor:
+        if self.master is not None:
+            return self.view_alloc(self.master, name)
+        o, s = self.small_offsets[name], self.alloc_shapes[name]
+        return self.small[o:o + math.prod(s)].view(s)
+
+    def pview_span(self, first: str, shape: tuple[int, ...]) -> torch.Tensor:
+        if self.master is not None:
+            return self.view_span(self.master, first, shape)
+        o = self.small_offsets[first]
+        return self.small[o:o + math.prod(shape)].view(shape)
+
+    def small_names(self) -> list[str]:
+        return [n for n in self.names if len(self.shapes[n]) < 2]
+
+    def drop_master(self, params: dict[str, nn.Parameter]) -> None:
+        """Free the full fp32 master: keep the 1-D parameters in `small` (same order, alloc sizes rounded up to ALIGN so that spans
+        of neighbouring 1-D parameters stay contiguous and 16-byte aligned), re-point the nn.Parameters at the 16-bit copy."""
+        off = 0
+        for n in self.small_names():
+            self.small_offsets[n] = off
+            off += (math.prod(self.alloc_shapes[n]) + ALIGN - 1) // ALIGN * ALIGN
+        self.small = torch.zeros(max(off, 1), dtype=torch.float32, device=self.master.device)
+        for n in self.small_names():
+            k = math.prod(self.alloc_shapes[n])
+            self.small[self.small_offsets[n]:self.small_offsets[n] + k].copy_(self.master[self.offsets[n]:self.offsets[n] + k])
+        self.master = None
+        for name, p_ in params.items():
+            p_.grad = None  # fp32 gradient views cannot hang off 16-bit parameters; the kernels reach them through gview()
+            p_.data = self.view(self.shadow, name)
+        self.master_stale = False
+
+    def materialize_master(self) -> torch.Tensor:
+        """Full fp32 parameter vector (flat layout): the master itself, or — sharded — a fresh copy all-gathered from the owners
+        (collective: every rank must call it)."""
+        if self.master is not None:
+            self.consolidate()
+            return self.master
+        if self.master_materializer is None:
+            raise RuntimeError("the fp32 master was dropped but no materializer is installed")
+        return self.master_materializer()
 
     # ---- gradient views (through the router when the engine shards gradients)
     def _gbuf(self, name: str) -> tuple[torch.Tensor, int]:
@@ -109,6 +171,8 @@ class FlatParams:
 
     def apply(self, fn) -> None:
         """Move/cast the buffers (used by nn.Module._apply: .to(), .cuda()). The master stays fp32."""
+        if self.master is None:
+            raise RuntimeError("a module whose fp32 master is sharded by the TrainEngine cannot be moved or cast")
         new_master = fn(self.master)
         if new_master.dtype != torch.float32:
             raise TypeError("B200 modules keep fp32 master parameters; bf16 compute copies are managed internally "
@@ -141,6 +205,8 @@ class FlatParams:
     def sync_shadow(self, force: bool = False) -> None:
         """Refresh the bf16 compute copy if the fp32 master was modified through torch (load_state_dict, a torch
         optimizer, manual edits). The fused Adam keeps both in step without bumping any version counter."""
+        if self.master is None:  # sharded master: the 16-bit copy is written by the optimizer / the loader, nothing to re-cast
+            return
         v = self.current_version()
         if force or v != self.shadow_version:
             # under ZeRO-1 a torch-side edit must rewrite the whole master on every rank (load_state_dict, broadcast);

@@ -339,9 +339,9 @@ def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None, dropout_
 
 # ----------------------------------------------------------------------------------------------------- Optimizer
 def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_group, groups, grad_scale=None, zero_grad=False,
-              chunk_state=None, skip_flag=None, g_packed=False):
+              chunk_state=None, skip_flag=None, g_packed=False, p_packed=False):
     """p_bf16: the 16-bit compute copy (bf16 or fp16; its dtype selects the library build). skip_flag (device int32, optional):
-    non-zero leaves p, m, v untouched (fp16 overflow step). g_packed: g is a packed shard buffer indexed like m / v (ZeRO-2)."""
+    non-zero leaves p, m, v untouched (fp16 overflow step). g_packed / p_packed: g / p are packed shard buffers indexed like m / v (ZeRO-2 gradients / a sharded fp32 master)."""
     n_chunks = chunk_start.numel()
     arr = (AdamGroup * len(groups))()
     for i, gdict in enumerate(groups):
@@ -351,7 +351,7 @@ def adam_step(p, g, m, v, p_bf16, state_base, chunk_start, chunk_len, chunk_grou
     lib = _L(p_bf16) if p_bf16 is not None else _L(p)
     check(lib.b200_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), int(state_base), ptr(chunk_start), ptr(chunk_len),
                              ptr(chunk_group), ptr(chunk_state), n_chunks, arr, len(groups), ptr(grad_scale), int(zero_grad),
-                             ptr(skip_flag), int(g_packed), stream_ptr()), "b200_adam_step")
+                             ptr(skip_flag), int(g_packed), int(p_packed), stream_ptr()), "b200_adam_step")
     _count(1)
 
 

@@ -108,19 +108,40 @@ class _FlatModule(nn.Module):
     def state_dict(self, *args, **kwargs):
         # ZeRO-1 replicates only the bf16 compute copy between steps; bring every rank's fp32 master up to date first
         # (a collective: like DeepSpeed's consolidated state_dict, all ranks must call it)
+        if self.flat.master is None:  # sharded master: fp32 values all-gathered from their owners into a fresh full copy
+            from collections import OrderedDict
+
+            full = self.flat.materialize_master()
+            prefix = kwargs.get("prefix", args[1] if len(args) > 1 else "")
+            return OrderedDict((prefix + n, self.flat.view(full, n)) for n, _ in self.named_parameters())
         self.flat.consolidate()
         return super().state_dict(*args, **kwargs)
 
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        if self.flat.master is None:  # sharded master: scatter a full fp32 copy back to the owners (collective)
+            full = self.flat.materialize_master()
+            own = [n for n, _ in self.named_parameters()]
+            missing = [n for n in own if n not in state_dict]
+            if strict and missing:
+                raise KeyError(f"missing keys: {missing[:4]}")
+            with torch.no_grad():
+                for n in own:
+                    if n in state_dict:
+                        self.flat.view(full, n).copy_(state_dict[n].to(torch.float32))
+            self.flat.master_loader(full)
+            return None
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
+
     def _ensure_grads_attached(self) -> None:
-        if self.flat.grad is None:  # ZeRO-2: gradients live in transient bucket buffers / the engine's shard accumulator
-            return
+        if self.flat.grad is None or self.flat.master is None:
+            return  # ZeRO-2 (gradients live in transient bucket buffers / the shard accumulator) or a sharded master (16-bit parameters)
         for name, p in self.named_parameters():
             if p.grad is None:
                 p.grad = self.flat.view(self.flat.grad, name)
 
     def _grads_were_dropped(self) -> bool:
         """A foreign zero_grad(set_to_none=True) (torch optimizers, nn.Module default) drops the views: treat as zero."""
-        if self.flat.grad is None:
+        if self.flat.grad is None or self.flat.master is None:
             return False
         p = next(self.parameters())
         return p.grad is None
@@ -234,7 +255,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
 
     @property
     def device(self) -> torch.device:
-        return self.flat.master.device
+        return self.flat.device
 
     @property
     def dtype(self) -> torch.dtype:
@@ -262,8 +283,8 @@ class B200GPTNeoXForCausalLM(_FlatModule):
     def _w(self, name: str) -> torch.Tensor:  # bf16 compute copy
         return self.flat.view(self.flat.shadow, name)
 
-    def _p(self, name: str) -> torch.Tensor:  # fp32 master (LayerNorm affine, biases)
-        return self.flat.view(self.flat.master, name)
+    def _p(self, name: str) -> torch.Tensor:  # fp32 values the kernels read directly (LayerNorm affine, biases)
+        return self.flat.pview(name)
 
     def _g(self, name: str) -> torch.Tensor:  # fp32 gradient accumulator
         return self.flat.gview(name)
@@ -401,7 +422,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
             hook(*self.flat.range_of(["gpt_neox.embed_in.weight"]))
 
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor | None = None, attention_mask: torch.Tensor | None = None, **_unused):
-        if not self.flat.master.is_cuda:
+        if self.flat.device.type != "cuda":
             raise RuntimeError("B200GPTNeoXForCausalLM runs only on a CUDA (sm_100a) device: there is no CPU fallback. "
                                "Move the module with .cuda() first.")
         if attention_mask is not None and not bool(attention_mask.all()):

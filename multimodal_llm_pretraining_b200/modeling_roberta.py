@@ -198,7 +198,7 @@ class B200RobertaForMaskedLM(_FlatModule):
 
     @property
     def device(self) -> torch.device:
-        return self.flat.master.device
+        return self.flat.device
 
     @property
     def dtype(self) -> torch.dtype:
@@ -218,7 +218,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         return self.flat.view(self.flat.shadow, name)
 
     def _p(self, name):
-        return self.flat.view(self.flat.master, name)
+        return self.flat.pview(name)
 
     def _g(self, name):
         return self.flat.gview(name)
@@ -256,7 +256,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         p = f"roberta.encoder.layer.{i}"
         h, nh, hd = self.h, self.nh, self.hd
         drop = train and self.p_hidden > 0.0
-        qkv = K.gemm(x, self._qkv_w(p), bias=self._qkv_b(p, self.flat.master))  # [T, 3h] = q | k | v
+        qkv = K.gemm(x, self._qkv_w(p), bias=self.flat.pview_span(f"{p}.attention.self.query.bias", (3 * self.h,)))  # [T, 3h] = q | k | v
         q4 = qkv.view(B, S, 3, nh, hd)
         pa = self.p_attn if train else 0.0
         o, lse = K.attention_fwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=False, scale=hd ** -0.5, dropout_p=pa, dropout_seed=self._seed(4 * i + 3))
@@ -329,7 +329,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         d = K.gemm(x, self._w("lm_head.dense.weight"), bias=self._p("lm_head.dense.bias"), gelu=True, aux_out=d_pre)
         n, _, mean, rstd = K.layernorm_fwd(d, self._p("lm_head.layer_norm.weight"), self._p("lm_head.layer_norm.bias"), self.eps)
         w_dec = self.flat.view_alloc(self.flat.shadow, "roberta.embeddings.word_embeddings.weight")  # [Vp, h], zero padding
-        b_dec = self.flat.view_alloc(self.flat.master, "lm_head.bias")
+        b_dec = self.flat.pview_alloc("lm_head.bias")
         logits = K.gemm(n, w_dec, bias=b_dec)  # [T, Vp] bf16
         return logits, (x, d_pre, d, n, mean, rstd)
 
@@ -397,7 +397,7 @@ class B200RobertaForMaskedLM(_FlatModule):
 
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor | None = None, attention_mask: torch.Tensor | None = None,
                 token_type_ids: torch.Tensor | None = None, **_unused):
-        if not self.flat.master.is_cuda:
+        if self.flat.device.type != "cuda":
             raise RuntimeError("B200RobertaForMaskedLM runs only on a CUDA (sm_100a) device: there is no CPU fallback. "
                                "Move the module with .cuda() first.")
         if attention_mask is not None and not bool(attention_mask.all()):

@@ -50,11 +50,12 @@ class B200Adam(torch.optim.Optimizer):
         self._step = 0
         self._built_for = None
         self._m = self._v = None
+        self._p32 = None  # sharded fp32 master (engine shard_master=True): the owned slices, packed like the moments
 
     # ------------------------------------------------------------------ chunk table / state
     def _build(self) -> None:
         f: FlatParams = self._flat
-        dev = f.master.device
+        dev = f.device
         ranges = self._ranges()
         # state offset of each owned range: ranges are packed back to back in the (sharded) moment buffers
         state_off, acc = [], 0
@@ -83,7 +84,7 @@ class B200Adam(torch.optim.Optimizer):
             self._v = torch.zeros(acc, dtype=torch.float32, device=dev)
             if m_old is not None and m_old.numel() == acc:
                 self._m.copy_(m_old), self._v.copy_(v_old)
-        self._built_for = (dev, f.master.data_ptr(), tuple(ranges))
+        self._built_for = (dev, f.shadow.data_ptr(), tuple(ranges))
 
     def _ranges(self) -> list[tuple[int, int]]:
         if self._shard is None:
@@ -110,8 +111,21 @@ class B200Adam(torch.optim.Optimizer):
 
     def _ensure_built(self) -> None:
         f = self._flat
-        if self._built_for != (f.master.device, f.master.data_ptr(), tuple(self._ranges())):
+        if self._built_for != (f.device, f.shadow.data_ptr(), tuple(self._ranges())):
             self._build()
+
+    def adopt_master_shard(self) -> torch.Tensor:
+        """True ZeRO partition of the fp32 weights: copy the slices this rank owns out of the (still full) flat master into a packed
+        buffer laid out like the moments; from now on the update reads and writes THAT (the engine then frees the full master)."""
+        f = self._flat
+        self._ensure_built()
+        ranges = self._ranges()
+        self._p32 = torch.empty(sum(hi - lo for lo, hi in ranges), dtype=torch.float32, device=f.device)
+        off = 0
+        for lo, hi in ranges:
+            self._p32[off:off + hi - lo].copy_(f.master[lo:hi])
+            off += hi - lo
+        return self._p32
 
     # ------------------------------------------------------------------ torch.optim API
     @torch.no_grad()
@@ -125,7 +139,7 @@ class B200Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         f = self._flat
-        if not f.master.is_cuda:
+        if f.device.type != "cuda":
             raise RuntimeError("B200Adam needs the module on a CUDA (sm_100a) device; there is no CPU fallback")
         self._ensure_built()
         self._step += 1
@@ -139,9 +153,10 @@ class B200Adam(torch.optim.Optimizer):
             grad_scale = f.pending_grad_scale
         f.pending_grad_scale = None
         f.sync_shadow()  # no-op unless the master was edited through torch since the last step
-        K.adam_step(f.master, f.grad if grads is None else grads, self._m, self._v, f.shadow, self._state_base, self._chunk_start,
-                    self._chunk_len, self._chunk_group, groups, grad_scale=grad_scale, zero_grad=self._zero_grad_in_step,
-                    chunk_state=self._chunk_state, skip_flag=skip_flag, g_packed=grads_packed)
+        K.adam_step(f.master if self._p32 is None else self._p32, f.grad if grads is None else grads, self._m, self._v, f.shadow,
+                    self._state_base, self._chunk_start, self._chunk_len, self._chunk_group, groups, grad_scale=grad_scale,
+                    zero_grad=self._zero_grad_in_step, chunk_state=self._chunk_state, skip_flag=skip_flag, g_packed=grads_packed,
+                    p_packed=self._p32 is not None)
         return loss
 
     def zero_grad(self, set_to_none: bool = False) -> None:

@@ -190,7 +190,7 @@ def _toy_classes():
             f = model.flat
             leaves = {}
             for n in f.names:  # 2-D from the bf16 compute copy, 1-D from the fp32 master
-                src = f.view(f.shadow, n).float() if len(f.shapes[n]) == 2 else f.view(f.master, n).clone()
+                src = f.view(f.shadow, n).float() if len(f.shapes[n]) == 2 else f.pview(n).clone()
                 leaves[n] = src.requires_grad_(True)
             with torch.enable_grad():
                 h = torch.tanh(leaves["emb.weight"][x] @ leaves["l0.weight"].t() + leaves["l0.bias"])
@@ -244,6 +244,11 @@ def _toy_classes():
             self.ranges = [tuple(r) for r in ranges]
             n = sum(hi - lo for lo, hi in self.ranges)
             self._m, self._v = torch.zeros(n), torch.zeros(n)
+            self._p32 = None
+
+        def adopt_master_shard(self):  # sharded fp32 master: the owned slices packed like the moments
+            self._p32 = torch.cat([self.flat.master[lo:hi] for lo, hi in self.ranges]).clone()
+            return self._p32
 
         def step(self, grads=None, grads_packed=False):
             f = self.flat
@@ -254,8 +259,9 @@ def _toy_classes():
             for lo, hi in self.ranges:
                 n = hi - lo
                 g = grads[off:off + n] if grads_packed else f.grad[lo:hi]  # ZeRO-2: packed shard accumulator, laid out like m / v
-                _adam_ref(f.master[lo:hi], g * scale, self._m[off:off + n], self._v[off:off + n], self.t, lr=self.lr)
-                f.shadow[lo:hi] = f.master[lo:hi].to(torch.bfloat16)
+                pm = f.master[lo:hi] if self._p32 is None else self._p32[off:off + n]
+                _adam_ref(pm, g * scale, self._m[off:off + n], self._v[off:off + n], self.t, lr=self.lr)
+                f.shadow[lo:hi] = pm.to(torch.bfloat16)
                 off += n
 
         def state_dict(self):
@@ -323,6 +329,30 @@ def _engine_worker(rank, world, port, q, tmpdir):
         ref = finals["ddp"]["master"]
         err = ((model.flat.master - ref).norm() / (ref - Toy().flat.master).norm()).item()
         assert err < 1e-5, err
+
+        # sharded fp32 master (true ZeRO partition of the weights): no full master after construction, parameters are views of the
+        # 16-bit copy, fp32 1-D parameters replicated in flat.small; state_dict materialises fp32 from the owners and must equal DDP
+        for strategy in ("zero1", "zero2"):
+            model = Toy()
+            eng = TrainEngine(model, ToyAdam(model.flat), None, max_grad_norm=0.05, gradient_accumulation_steps=2, strategy=strategy, shard_master=True)
+            f = model.flat
+            assert f.master is None and eng.optimizer._p32.numel() == sum(hi - lo for lo, hi in eng.plan.owned_ranges())
+            assert all(p.dtype == torch.bfloat16 and p.grad is None for p in model.parameters())
+            run(eng, range(3))
+            sd = model.state_dict()
+            full = torch.cat([sd[n].reshape(-1) for n in f.names])
+            want = torch.cat([f.view(finals["ddp"]["master"], n).reshape(-1) for n in f.names])
+            if strategy == "zero1":
+                assert torch.equal(full, want), (full - want).abs().max()
+            else:
+                assert ((full - want).norm() / (want - torch.cat([Toy().flat.view(Toy().flat.master, n).reshape(-1) for n in f.names])).norm()).item() < 1e-5
+            assert torch.equal(f.shadow, finals["ddp"]["shadow"]) or strategy == "zero2"
+            # load_state_dict scatters a full fp32 copy back to the owners: a perturbed copy round-trips
+            sd2 = {k: v + 0.5 for k, v in sd.items()}
+            model.load_state_dict(sd2)
+            again = model.state_dict()
+            assert all(torch.equal(again[k], sd2[k]) for k in sd2)
+            assert torch.equal(f.pview("l0.bias"), sd2["l0.bias"])
 
         # ZeRO-1 checkpoint: 2 steps, save, fresh engine (different init), load, third step == uninterrupted
         model = Toy()
