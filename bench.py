@@ -45,6 +45,9 @@ def parse():
                     help="bf16 (every BASELINE.json config) or fp16 + dynamic loss scaling (the reference's own precision for Pythia != 1b / RoBERTa)")
     ap.add_argument("--batch-preserving", action="store_true",
                     help="grad-acc = 1024 / (gpus * mbs): the reference's rule W * mbs * ga = batch_size (src/models/__init__.py:99-102)")
+    ap.add_argument("--shard-master", action="store_true",
+                    help="ZeRO-1/2 only: shard the fp32 master too (each rank keeps the fp32 weights of the slices it owns; parameters become "
+                         "views of the 16-bit copy), i.e. DeepSpeed's 12 B/param/W of optimizer state per rank")
     ap.add_argument("--phases", action="store_true",
                     help="after the timed region, one more instrumented step: per-rank micro-batch and optimizer-phase device times in the JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,7 +267,8 @@ def main_b200(a):
     skw = dict(mc.scheduler_kwargs)
     warm = skw.pop("num_warmup_steps", 0)
     sched = get_scheduler(mc.scheduler_type, opt, warm, mc.training_steps, skw)
-    eng = TrainEngine(model, opt, sched, max_grad_norm=mc.max_grad_norm, gradient_accumulation_steps=a.grad_acc, strategy=strategy)
+    eng = TrainEngine(model, opt, sched, max_grad_norm=mc.max_grad_norm, gradient_accumulation_steps=a.grad_acc, strategy=strategy,
+                      shard_master=a.shard_master)
 
     ga, mbs = a.grad_acc, a.mbs
     total_steps = a.warmup + a.steps
@@ -384,6 +388,7 @@ def main_b200(a):
                             f"+ clip + fused Adam (random-init weights, uniform random tokens)",
                 "model": a.model, "micro_batch": mbs, "grad_acc": ga, "global_batch_sequences": world * ga * mbs,
                 "seq_len": S_in, "parallelism": f"{strategy}x{world}", "activation_checkpointing": bool(a.checkpointing), "precision": a.precision,
+                "fp32_master": "sharded" if eng.shard_master else "replicated",
                 **({"note": "hidden dropout 0.1 and attention-probability dropout 0.1 applied (roberta-large config)"} if is_roberta else {}),
                 "l2": "working set per step (>= 2 GB of weights, > 30 GB of activations) far exceeds the 126 MB L2; no explicit flush",
             },
@@ -391,6 +396,9 @@ def main_b200(a):
                     "ms_per_step": ms_e2e / a.steps, "last_loss": last_loss},
             "gpu_launches": launches,
             "clocks": clocks,
+            "memory": {"rank0_max_allocated_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+                       "rank0_parameter_state_gb": sum(t.numel() * t.element_size() for t in (model.flat.master, model.flat.grad, model.flat.shadow, model.flat.small,
+                                                                                               opt._m, opt._v, opt._p32, getattr(eng, "_gshard", None)) if t is not None) / 1e9},
             "mfu": {
                 "flops_per_token": f_tok, "tflops_per_gpu": per_gpu * f_tok / 1e12,
                 "vs_datasheet_2250": per_gpu * f_tok / 1e12 / 2250.0, "vs_measured_sustained": per_gpu * f_tok / 1e12 / peak_sust,
