@@ -204,8 +204,9 @@ def _toy_classes():
             model, f = ctx.model, ctx.model.flat
             names = list(ctx.leaves)
             grads = torch.autograd.grad(ctx.loss, [ctx.leaves[n] for n in names], grad_out)
+            scale = getattr(model, "loss_scale", None)  # fp16 runs: the engine's device-side loss scale multiplies every gradient
             for n, g in zip(names, grads):
-                f.gview(n).add_(g)  # the flat gradient buffer, or the engine's transient bucket buffer under ZeRO-2
+                f.gview(n).add_(g if scale is None else g * float(scale))  # the flat gradient buffer, or the engine's transient bucket buffer under ZeRO-2
             if model.grad_ready_hook:
                 for b in model.comm_buckets():  # backward order: head first, embedding last
                     model.grad_ready_hook(*b)
@@ -380,6 +381,133 @@ def test_train_engine_zero1_equals_ddp_and_resumes_world2(tmp_path):
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000
     procs = [ctx.Process(target=_engine_worker, args=(r, 2, port, q, str(tmp_path / "ckpt"))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp16 overflow handling across ranks: a non-finite gradient on ONE rank must skip the optimizer step on EVERY rank (the flag comes
+# from the all-reduced gradients under DDP and from the all-reduced sum of squares under ZeRO), leave parameters and moments
+# untouched, clear the accumulators (the ZeRO-2 shard too), back the loss scale off once, and keep the scheduler where it was.
+# clip_coef / loss_scale_update are torch statements of adam.cu's clip_coef_kernel / loss_scale_update_kernel.
+# ---------------------------------------------------------------------------------------------------------------
+def _clip_coef_ref(sumsq, max_norm, loss_scale=None, found_inf=None):
+    s = float(loss_scale) if loss_scale is not None else 1.0
+    if found_inf is not None:
+        found_inf.fill_(0 if bool(torch.isfinite(sumsq)) else 1)
+    norm = sumsq.sqrt() / s
+    coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0) if max_norm and max_norm > 0 else torch.ones(())
+    return norm, coef / s
+
+
+def _loss_scale_update_ref(scale, tracker, hyst_left, found_inf, growth_factor, backoff_factor, growth_interval, min_scale, hysteresis):
+    if int(found_inf):
+        left = int(hyst_left) - 1
+        if hysteresis <= 1 or left <= 0:
+            scale.fill_(max(float(scale) * backoff_factor, min_scale))
+            left = hysteresis if hysteresis <= 1 else 1
+        hyst_left.fill_(left)
+        tracker.zero_()
+    else:
+        t = int(tracker) + 1
+        if t >= growth_interval:
+            scale.mul_(growth_factor)
+            tracker.zero_()
+            hyst_left.fill_(hysteresis)
+        else:
+            tracker.fill_(t)
+
+
+def _overflow_worker(rank, world, port, q, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import multimodal_llm_pretraining_b200.kernels as K
+        from multimodal_llm_pretraining_b200.engine import LossScaler, TrainEngine
+
+        K.sumsq_ = lambda x, out: out.add_((x.double() ** 2).sum().float())
+        K.clip_coef = _clip_coef_ref
+        K.loss_scale_update = _loss_scale_update_ref
+        Toy, ToyAdam = _toy_classes()
+        g = torch.Generator().manual_seed(100)
+        xs = torch.randint(0, 32, (4, 2, world, 16), generator=g)
+        ys = torch.randn(4, 2, world, 16, 4, generator=g)
+        ys[1, 0, 1, 3, 2] = float("inf")  # step 1, first micro-batch, rank 1 only
+
+        class Sched:
+            n = 0
+
+            def step(self):
+                self.n += 1
+
+            def state_dict(self):
+                return {"n": self.n}
+
+            def load_state_dict(self, sd):
+                self.n = sd["n"]
+
+        finals = {}
+        for strategy in ("ddp", "zero1", "zero2"):
+            model, sched = Toy(), Sched()
+            scaler = LossScaler("cpu", kind="torch", init_scale=1024.0, growth_interval=2)
+            eng = TrainEngine(model, ToyAdam(model.flat), sched, max_grad_norm=0.05, gradient_accumulation_steps=2, strategy=strategy,
+                              loss_scaler=scaler)
+            assert model.loss_scale is scaler.scale
+            f, done = model.flat, []
+            for s in range(4):
+                for m in range(2):
+                    eng.manual_training_step({"input_ids": xs[s, m, rank], "labels": ys[s, m, rank]})
+                if s == 1:
+                    model.state_dict()  # consolidates the fp32 master under ZeRO-1/2
+                    before = (f.master.clone(), f.shadow.clone(), eng.optimizer._m.clone(), eng.optimizer._v.clone())
+                ok = eng.manual_optimization_step()
+                done.append(ok)
+                votes = torch.tensor([int(ok)])
+                dist.all_reduce(votes)
+                assert int(votes) in (0, world), "ranks disagree about skipping step %d" % s
+                if s == 1:
+                    assert not ok and float(scaler.scale) == 512.0 and scaler.skipped_steps == 1 and int(scaler.growth_tracker) == 0
+                    assert eng.optimizer.t == 1 and sched.n == 1
+                    model.state_dict()
+                    after = (f.master, f.shadow, eng.optimizer._m, eng.optimizer._v)
+                    assert all(torch.equal(a, b) for a, b in zip(before, after)), "a skipped step must not move parameters or moments"
+                    acc = eng._gshard if strategy == "zero2" else f.grad
+                    assert float(acc.abs().max()) == 0.0 and f.pending_grad_scale is None
+                    if strategy == "zero1":  # checkpoint carries the backed-off scale
+                        eng.save_checkpoint(tmpdir)
+                        model2 = Toy(seed=3)
+                        eng2 = TrainEngine(model2, ToyAdam(model2.flat), Sched(), max_grad_norm=0.05, gradient_accumulation_steps=2,
+                                           strategy=strategy, loss_scaler=LossScaler("cpu", kind="torch", init_scale=1024.0, growth_interval=2))
+                        eng2.load_checkpoint(tmpdir)
+                        assert float(eng2.loss_scaler.scale) == 512.0 and eng2.loss_scaler.skipped_steps == 1
+            assert done == [True, False, True, True]
+            assert float(scaler.scale) == 1024.0 and eng.optimizer.t == 3 and sched.n == 3  # two clean steps after the back-off: grown again
+            model.state_dict()
+            assert bool(torch.isfinite(f.master).all())
+            finals[strategy] = f.master.clone()
+        # power-of-two scales are exact in fp32, so the scaled ZeRO-1 run is the scaled DDP run bit for bit
+        assert torch.equal(finals["zero1"], finals["ddp"])
+        moved = (finals["ddp"] - Toy().flat.master).norm()
+        assert ((finals["zero2"] - finals["ddp"]).norm() / moved).item() < 1e-5
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "".join(traceback.format_exception(e))[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fp16_overflow_on_one_rank_skips_the_step_everywhere_world2(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_overflow_worker, args=(r, 2, port, q, str(tmp_path / "ckpt"))) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
