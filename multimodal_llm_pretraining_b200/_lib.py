@@ -51,7 +51,6 @@ class AttnArgs(C.Structure):
         ("dqkv_row_stride", c_int64), ("dqkv_head_stride", c_int64),
         ("p_scratch", c_void_p), ("ds_scratch", c_void_p),
         ("dropout_p", c_float), ("dropout_seed", C.c_uint64),
-        ("colsum_out", c_void_p),
     ]
 
 

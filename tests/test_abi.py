@@ -21,6 +21,28 @@ def test_header_and_binding_agree():
     assert sorted(_lib.SIGNATURES) == declared
 
 
+def _declared_prototypes():
+    """name -> number of parameters, parsed from the header's prototypes."""
+    text = (ROOT / "include" / "b200pt.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    for m in re.finditer(r"\b(b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_binding_argument_counts_match_the_header():
+    """ctypes does not check arity against the C prototype: a drifted binding would pass garbage in the trailing arguments."""
+    from multimodal_llm_pretraining_b200 import _lib
+
+    protos = _declared_prototypes()
+    assert sorted(protos) == _declared_symbols()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == protos[name], (name, len(argtypes), protos[name])
+
+
 def test_library_loads_and_exports_everything():
     from multimodal_llm_pretraining_b200 import _lib
     from multimodal_llm_pretraining_b200.csrc import build
@@ -32,6 +54,20 @@ def test_library_loads_and_exports_everything():
     assert lib.b200_abi_version() == _lib.ABI_VERSION
 
 
+def test_fp16_twin_exports_the_same_abi():
+    """libb200pt_fp16.so = the same sources with -DB200_ELEM_FP16: same symbols and version, a different element type tag."""
+    from multimodal_llm_pretraining_b200 import _lib
+    from multimodal_llm_pretraining_b200.csrc import build
+
+    build.build()
+    bf, fp = _lib.load(), _lib.load("fp16")
+    assert _lib.LIB_PATH_FP16.exists() and bf is not fp
+    for name in _declared_symbols():
+        assert hasattr(fp, name), name
+    assert fp.b200_abi_version() == bf.b200_abi_version() == _lib.ABI_VERSION
+    assert bf.b200_elem_dtype() != fp.b200_elem_dtype()
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
 
@@ -41,3 +77,32 @@ def test_product_path_fails_loudly_without_gpu():
 
     with pytest.raises(_lib.B200Error):
         _lib.lib_for(0)
+
+
+def test_ctypes_structs_match_the_c_layout(tmp_path):
+    """Every field of the three argument structs sits at the offset the C compiler gives it (gcc on include/b200pt.h)."""
+    import shutil
+    import subprocess
+
+    from multimodal_llm_pretraining_b200 import _lib
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = [("b200_gemm_args", _lib.GemmArgs), ("b200_attn_args", _lib.AttnArgs), ("b200_adam_group", _lib.AdamGroup)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "b200pt.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        import ctypes
+
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
