@@ -152,6 +152,12 @@ class _FlatModule(nn.Module):
     grad_ready_hook = None
     param_wait_hook = None
 
+    def _require_cuda(self) -> None:
+        """The kernels exist for sm_100a only; fail before any of them is reached with a message that says what to do."""
+        if self.flat.device.type != "cuda":
+            raise RuntimeError(f"{type(self).__name__} runs only on a CUDA (sm_100a) device: there is no CPU fallback. "
+                               "Move the module with .cuda() first.")
+
     def _wait_bucket(self, rng: tuple[int, int]) -> None:
         if self.param_wait_hook is not None:
             self.param_wait_hook(*rng)
@@ -422,9 +428,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
             hook(*self.flat.range_of(["gpt_neox.embed_in.weight"]))
 
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor | None = None, attention_mask: torch.Tensor | None = None, **_unused):
-        if self.flat.device.type != "cuda":
-            raise RuntimeError("B200GPTNeoXForCausalLM runs only on a CUDA (sm_100a) device: there is no CPU fallback. "
-                               "Move the module with .cuda() first.")
+        self._require_cuda()
         if attention_mask is not None and not bool(attention_mask.all()):
             raise NotImplementedError("padding masks are not on the reference's benchmarked path (src/benchmarking/data.py:8-21)")
         self.flat.sync_shadow()

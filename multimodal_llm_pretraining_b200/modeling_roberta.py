@@ -397,9 +397,7 @@ class B200RobertaForMaskedLM(_FlatModule):
 
     def forward(self, input_ids: torch.Tensor, labels: torch.Tensor | None = None, attention_mask: torch.Tensor | None = None,
                 token_type_ids: torch.Tensor | None = None, **_unused):
-        if self.flat.device.type != "cuda":
-            raise RuntimeError("B200RobertaForMaskedLM runs only on a CUDA (sm_100a) device: there is no CPU fallback. "
-                               "Move the module with .cuda() first.")
+        self._require_cuda()
         if attention_mask is not None and not bool(attention_mask.all()):
             raise NotImplementedError("padding masks are not on the reference's benchmarked path (src/benchmarking/data.py:8-21)")
         if token_type_ids is not None and bool(token_type_ids.any()):

@@ -127,6 +127,10 @@ class B200Adam(torch.optim.Optimizer):
             off += hi - lo
         return self._p32
 
+    def _require_cuda(self) -> None:
+        if self._flat.device.type != "cuda":
+            raise RuntimeError("B200Adam needs the module on a CUDA (sm_100a) device; there is no CPU fallback")
+
     # ------------------------------------------------------------------ torch.optim API
     @torch.no_grad()
     def step(self, closure=None, grad_scale: torch.Tensor | None = None, skip_flag: torch.Tensor | None = None,
@@ -139,8 +143,7 @@ class B200Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         f = self._flat
-        if f.device.type != "cuda":
-            raise RuntimeError("B200Adam needs the module on a CUDA (sm_100a) device; there is no CPU fallback")
+        self._require_cuda()
         self._ensure_built()
         self._step += 1
         t = self._step
