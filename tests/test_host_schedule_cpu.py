@@ -167,3 +167,224 @@ def test_neox_eval_and_logits_paths(K, gold):
     assert rel(full[:, :-1], out.logits) <= 1e-6  # causal: dropping the last token does not change the others
     if "logits0" in gold:
         assert rel(full, gold["logits0"]) <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------------------- RoBERTa
+@pytest.fixture(scope="module")
+def gold_r():
+    return torch.load(GOLD_ROBERTA, map_location="cpu", weights_only=False)
+
+
+def _roberta(gold_r):
+    m = CpuRoberta(SimpleNamespace(**gold_r["cfg"]))
+    m.load_hf_state_dict(gold_r["state_dict"])
+    return m.train()
+
+
+def test_roberta_schedule_logits_loss_and_every_gradient_vs_hf_golden(K, gold_r):
+    m = _roberta(gold_r)
+    ids = gold_r["batches"][0]
+    m.eval()
+    assert rel(m(input_ids=ids, labels=ids)["logits"], gold_r["logits0"]) <= 2e-2
+    m.train()
+    loss = m(input_ids=ids, labels=ids)["loss"]
+    assert abs(loss.item() - gold_r["loss0"].item()) <= 5e-3 * gold_r["loss0"].item()
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    for k, g in gold_r["grads0"].items():
+        if k.endswith("attention.self.key.bias"):  # analytically zero (tests/test_roberta_gpu.py)
+            qn = gold_r["grads0"][k.replace("key.bias", "query.bias")].norm().item()
+            assert grads[k].float().norm().item() <= 2e-2 * qn, k
+            continue
+        assert rel(grads[k], g) <= 5e-2, (k, rel(grads[k], g))
+
+
+def test_roberta_three_fused_adamw_steps_vs_hf_golden(K, gold_r):
+    m = _roberta(gold_r)
+    opt = CpuAdam(m.parameters(), lr=4e-4, betas=(0.9, 0.98), weight_decay=0.0)
+    losses = []
+    for b in gold_r["batches"]:
+        loss = m(input_ids=b, labels=b)["loss"]
+        loss.backward()
+        opt.step()
+        m.zero_grad()
+        losses.append(loss.item())
+    for a, b in zip(losses, gold_r["losses_3steps"].tolist()):
+        assert abs(a - b) <= 1e-2 * b, (losses, gold_r["losses_3steps"].tolist())
+    sd = m.state_dict()
+    for k in ("roberta.encoder.layer.1.intermediate.dense.weight", "roberta.embeddings.word_embeddings.weight", "lm_head.bias"):
+        upd, ref_upd = sd[k] - gold_r["state_dict"][k], gold_r["state_dict_after3"][k] - gold_r["state_dict"][k]
+        assert rel(upd, ref_upd) <= 0.25, (k, rel(upd, ref_upd))
+    f = m.flat  # the vocabulary padding behind the embedding matrix / decoder bias stays exactly zero
+    assert torch.all(f.view_alloc(f.master, "roberta.embeddings.word_embeddings.weight")[m.V:] == 0)
+    assert torch.all(f.view_alloc(f.master, "lm_head.bias")[m.V:] == 0)
+
+
+def test_roberta_checkpointing_is_exact_and_buckets_fire_in_backward_order(K, gold_r):
+    ids = gold_r["batches"][0]
+    m = _roberta(gold_r)
+    m(input_ids=ids, labels=ids)["loss"].backward()
+    g0 = m.flat.grad.clone()
+    m.zero_grad()
+    m.gradient_checkpointing_enable()
+    fired = []
+    m.grad_ready_hook = lambda s, e: fired.append((s, e))
+    m(input_ids=ids, labels=ids)["loss"].backward()
+    assert torch.equal(m.flat.grad, g0)
+    assert fired == m.comm_buckets()
+    srt = sorted(fired)
+    assert srt[0][0] == 0 and all(a[1] == b[0] for a, b in zip(srt, srt[1:]))
+
+
+# ------------------------------------------------------------------------------------------------------------- TrainEngine, world 2
+# The CPU twin of scripts/dev/dp_check.py (which runs on 2 / 8 GPUs): the REAL NeoX and RoBERTa modules through the REAL TrainEngine over
+# gloo — DDP, ZeRO-1, ZeRO-2, the sharded fp32 master, activation checkpointing, fp16 + loss scaling — compared with a single-process
+# run over the same global batch and with each other.
+TINY = dict(vocab_size=256, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512, rotary_pct=0.25,
+            rotary_emb_base=10000, layer_norm_eps=1e-5)
+TINY_R = dict(vocab_size=301, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, max_position_embeddings=66,
+              type_vocab_size=1, pad_token_id=1, layer_norm_eps=1e-5, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+              hidden_act="gelu", initializer_range=0.02)
+
+
+def _build(kind="neox", seed=0):
+    m = CpuNeoX(SimpleNamespace(**TINY)) if kind == "neox" else CpuRoberta(SimpleNamespace(**TINY_R))
+    m.reset_parameters(torch.Generator().manual_seed(seed))
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(seed + 1)
+        for n, p in m.named_parameters():
+            if n.endswith(".bias"):
+                p.normal_(0, 0.02, generator=g)
+    m.flat.sync_shadow(force=True)
+    return m.train()
+
+
+def _noise_mask(m):
+    """False on the elements whose gradient is analytically zero (key biases): Adam turns their rounding noise into +-lr steps."""
+    keep = torch.ones(m.flat.numel, dtype=torch.bool)
+    for n, p in m.named_parameters():
+        _, off, cnt = p._b200_flat
+        if n.endswith("query_key_value.bias"):
+            keep[off:off + cnt].view(m.nh, 3, -1)[:, 1] = False
+        if n.endswith("attention.self.key.bias"):
+            keep[off:off + cnt] = False
+    return keep
+
+
+def _dp_worker(rank, world, port, q, tmpdir, kind):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cpu_kernels.install()
+        from multimodal_llm_pretraining_b200.engine import LossScaler, TrainEngine
+
+        steps, ga, B = 2, 2, 2
+        S = 17 if kind == "neox" else 16
+        V = TINY["vocab_size"] if kind == "neox" else TINY_R["vocab_size"]
+        data = torch.randint(2, V, (steps, ga, world, B, S), generator=torch.Generator().manual_seed(7))
+        Opt = CpuAdam if kind == "neox" else CpuAdamW
+
+        def train(strategy, **kw):
+            dtype = kw.pop("dtype", None)
+            ckpt = kw.pop("ckpt", False)
+            model = _build(kind)
+            if dtype is not None:
+                model.set_compute_dtype(dtype)
+                kw["loss_scaler"] = LossScaler("cpu", kind="torch", init_scale=256.0)
+            if ckpt:
+                model.gradient_checkpointing_enable()
+            opt = Opt(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+            if strategy == "none":  # one process, the whole global batch: micro-batches of every rank in turn
+                eng = TrainEngine(model, opt, None, max_grad_norm=0.5, gradient_accumulation_steps=ga * world, strategy="none", **kw)
+                for s in range(steps):
+                    for m in range(ga):
+                        for r in range(world):
+                            eng.manual_training_step({"input_ids": data[s, m, r], "labels": data[s, m, r]})
+                    assert eng.manual_optimization_step()
+            else:
+                eng = TrainEngine(model, opt, None, max_grad_norm=0.5, gradient_accumulation_steps=ga, strategy=strategy, **kw)
+                for s in range(steps):
+                    for m in range(ga):
+                        eng.manual_training_step({"input_ids": data[s, m, rank], "labels": data[s, m, rank]})
+                    assert eng.manual_optimization_step()
+            assert float(eng.last_grad_norm) > 0.5, "clipping must be active in this test"
+            full = model.flat.materialize_master().clone()
+            return model, eng, opt, full
+
+        init = _build(kind).flat.master.clone()
+        keep = _noise_mask(_build(kind))
+
+        def diff(a, b):
+            ua, ub = (a - init)[keep], (b - init)[keep]
+            return ((ua - ub).norm() / ub.norm()).item()
+
+        _, _, _, ref = train("none")
+        assert (ref - init).abs().max() > 1e-4
+        finals, norms = {}, {}
+        for strategy in ("ddp", "zero1", "zero2"):
+            model, eng, opt, full = train(strategy)
+            finals[strategy] = full
+            norms[strategy] = float(eng.last_grad_norm)
+            f = model.flat
+            assert torch.equal(f.shadow, full.to(f.shadow.dtype)), "16-bit compute copy != rounded fp32 master"
+            lst = [torch.empty_like(full) for _ in range(world)]
+            dist.all_gather(lst, full)
+            assert all(torch.equal(lst[0], x) for x in lst), "ranks hold different parameters"
+            # same mean gradient as the single-process run, summed in a different order, through bf16 activations
+            assert diff(full, ref) < 2e-2, (strategy, diff(full, ref))
+            if strategy != "ddp":
+                assert f.numel - 8 * 64 <= opt._m.numel() * world <= f.numel  # the store's tail padding belongs to no bucket
+            if strategy == "zero2":
+                assert f.grad is None and eng._gshard.numel() == opt._m.numel() and float(eng._gshard.abs().max()) == 0.0
+        # two-term sums are order independent: ZeRO-1's reduce-scatter and DDP's all-reduce give the same gradients; the norm is reduced in
+        # a different order (owned chunks + scalar all-reduce), so the clip coefficient may differ in the last ulp
+        assert diff(finals["zero1"], finals["ddp"]) < 1e-5
+        assert diff(finals["zero2"], finals["ddp"]) < 1e-2
+        # sharded fp32 master: the same arithmetic in a different place -> bit for bit, incl. a checkpoint round trip and the next step
+        for strategy in ("zero1", "zero2"):
+            model, eng, opt, full = train(strategy, shard_master=True)
+            assert model.flat.master is None and opt._p32.numel() == opt._m.numel()
+            assert torch.equal(full, finals[strategy]), strategy
+            eng.save_checkpoint(os.path.join(tmpdir, strategy))
+            m2 = _build(kind, seed=5)
+            o2 = Opt(m2.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+            e2 = TrainEngine(m2, o2, None, max_grad_norm=0.5, gradient_accumulation_steps=ga, strategy=strategy, shard_master=True)
+            e2.load_checkpoint(os.path.join(tmpdir, strategy))
+            assert torch.equal(m2.flat.materialize_master(), full) and torch.equal(m2.flat.shadow, model.flat.shadow)
+            for e_ in (eng, e2):
+                for m in range(ga):
+                    e_.manual_training_step({"input_ids": data[0, m, rank], "labels": data[0, m, rank]})
+                e_.manual_optimization_step()
+            assert torch.equal(m2.flat.materialize_master(), model.flat.materialize_master())
+        # activation checkpointing recomputes the same statements: bit-identical to the plain run of the same strategy
+        _, _, _, full = train("zero1", ckpt=True)
+        assert torch.equal(full, finals["zero1"])
+        # fp16 + loss scaling: a different rounding of the same computation (power-of-two scale: exact un-scaling)
+        model, eng, _, full = train("zero1", dtype=torch.float16)
+        assert model.flat.shadow.dtype == torch.float16 and eng.loss_scaler.skipped_steps == 0
+        # Adam's update is nearly invariant to the gradient scale, so the un-scaling is checked on the reported gradient norm ...
+        assert abs(float(eng.last_grad_norm) - norms["zero1"]) < 2e-2 * norms["zero1"], (float(eng.last_grad_norm), norms["zero1"])
+        # ... and the update against the bf16 run of the same strategy: two roundings (8 vs 11 significant bits) of one computation
+        assert diff(full, finals["zero1"]) < 0.15, diff(full, finals["zero1"])
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "".join(traceback.format_exception(e))[-2500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["neox", "roberta"])
+def test_real_modules_through_the_engine_world2(tmp_path, kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000 + (0 if kind == "neox" else 1)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, str(tmp_path), kind)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
