@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--mbs", type=int, default=None, help="micro-batch size (default 16 for Pythia, 64 for RoBERTa)")
     ap.add_argument("--grad-acc", type=int, default=16)
     ap.add_argument("--seq-len", type=int, default=None, help="RoBERTa only: 512 (default) or 128")
-    ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1", "zero2"])
+    ap.add_argument("--strategy", default=None, choices=[None, "none", "ddp", "zero1", "zero2", "zero3"])
     ap.add_argument("--checkpointing", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
                     help="bf16 (every BASELINE.json config) or fp16 + dynamic loss scaling (the reference's own precision for Pythia != 1b / RoBERTa)")
@@ -398,7 +398,7 @@ def main_b200(a):
             "clocks": clocks,
             "memory": {"rank0_max_allocated_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
                        "rank0_parameter_state_gb": sum(t.numel() * t.element_size() for t in (model.flat.master, model.flat.grad, model.flat.shadow, model.flat.small,
-                                                                                               opt._m, opt._v, opt._p32, getattr(eng, "_gshard", None)) if t is not None) / 1e9},
+                                                                                               opt._m, opt._v, opt._p32, getattr(eng, "_gshard", None), getattr(eng, "_w16", None)) if t is not None) / 1e9},
             "mfu": {
                 "flops_per_token": f_tok, "tflops_per_gpu": per_gpu * f_tok / 1e12,
                 "vs_datasheet_2250": per_gpu * f_tok / 1e12 / 2250.0, "vs_measured_sustained": per_gpu * f_tok / 1e12 / peak_sust,

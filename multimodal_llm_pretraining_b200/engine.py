@@ -1,4 +1,4 @@
-"""Data-parallel step engine: what HF Trainer + accelerate (DDP) / DeepSpeed (ZeRO-1, ZeRO-2) do for the benchmarked configs,
+"""Data-parallel step engine: what HF Trainer + accelerate (DDP) / DeepSpeed (ZeRO-1, ZeRO-2, ZeRO-3) do for the benchmarked configs,
 on top of the flat parameter store (src/train.py:126-181 selects the strategy declaratively in the reference;
 src/benchmarking/utils.py:61-80 drives it).
 
@@ -26,6 +26,14 @@ every rank runs independent micro-batches; the only exchange is per optimizer st
                      size), EVERY micro-batch the bucket is reduce-scattered (AVG) on the side stream as soon as the layer is
                      done, the owned slice is accumulated into a packed fp32 shard accumulator (4 B/param/W) and the buffer
                      is cleared for reuse. The optimizer step then runs on the shard accumulator (packed like the moments).
+
+  strategy "zero3" : parameter sharding on top (DeepSpeed stage 3 / FSDP full_shard, src/train.py:126-136,183-194): the fp32 master
+                     AND the 16-bit compute copy exist only as the slices a rank owns (18 B/param/W with moments and the gradient
+                     shard); the module announces each bucket right before it reads it, in forward and again in backward, and the
+                     engine all-gathers it into a transient buffer (ring of two per bucket size) while prefetching the next one of
+                     that direction on the side stream. GPT-NeoX modules only. Exercised with the real module over gloo on CPU
+                     (tests/test_host_schedule_cpu.py: equal to ZeRO-2 bit for bit, checkpoint round trip, activation
+                     checkpointing); NOT yet run on hardware, hence not selectable through the reference-facing `sharding=zero_3`.
 
 fp16 (the reference's precision for every Pythia but 1b and for RoBERTa): `LossScaler` keeps a dynamic loss scale on the
 device; the cross entropy folds it into dlogits, the clip-coefficient kernel divides it out again and reports overflow
@@ -112,6 +120,17 @@ class CommPlan:
         else:
             dist.all_gather_into_tensor(t, flat[lo:hi], group=self.group)
 
+    def all_gather_buffer(self, buf: torch.Tensor, own: torch.Tensor) -> None:
+        """buf (a whole bucket, W * own.numel() elements) <- the slices every rank owns, in rank order (ZeRO-3 weight gather)."""
+        if self._gloo():
+            parts = [torch.empty_like(own) for _ in range(self.W)]
+            dist.all_gather(parts, own.clone(), group=self.group)
+            n = own.numel()
+            for r, p_ in enumerate(parts):
+                buf[r * n:(r + 1) * n].copy_(p_)
+        else:
+            dist.all_gather_into_tensor(buf, own, group=self.group)
+
     def all_reduce_sum_scalar(self, x: torch.Tensor) -> None:
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
 
@@ -176,7 +195,9 @@ class TrainEngine:
     """manual_training_step / manual_optimization_step of the reference harness (src/benchmarking/utils.py:61-80) for a
     B200 module + B200Adam, with DDP, ZeRO-1 or ZeRO-2 over the flat buffers."""
 
-    STRATEGIES = ("none", "ddp", "zero1", "zero2")
+    STRATEGIES = ("none", "ddp", "zero1", "zero2", "zero3")
+    ZERO = ("zero1", "zero2", "zero3")          # optimizer state sharded
+    GRAD_SHARDED = ("zero2", "zero3")           # + gradients sharded (reduce-scatter every micro-batch)
 
     def __init__(self, model, optimizer, scheduler=None, max_grad_norm: float = 1.0, gradient_accumulation_steps: int = 1,
                  strategy: str = "none", group=None, overlap: bool = True, comm_max_ctas: int | None = None,
@@ -204,10 +225,13 @@ class TrainEngine:
         f = self.flat
         # fp16: a loss scale is mandatory (dlogits / n_valid underflow in half precision without it)
         if getattr(f, "compute_dtype", torch.bfloat16) == torch.float16 and loss_scaler is None and f.device.type == "cuda":
-            loss_scaler = LossScaler(f.device, kind="deepspeed" if strategy in ("zero1", "zero2") else "torch")
+            loss_scaler = LossScaler(f.device, kind="deepspeed" if strategy in self.ZERO else "torch")
         self.loss_scaler = loss_scaler
         if loss_scaler is not None:
             model.loss_scale = loss_scaler.scale
+        if strategy == "zero3" and not getattr(model, "supports_weight_sharding", False):
+            raise NotImplementedError(f"strategy 'zero3' needs a module whose backward announces its weight reads (param_bwd_hook); "
+                                      f"{type(model).__name__} does not")
         if strategy != "none":
             if not dist.is_initialized():
                 raise RuntimeError("strategy %r needs an initialised torch.distributed process group" % strategy)
@@ -224,7 +248,7 @@ class TrainEngine:
                 ranks = dist.get_process_group_ranks(group) if group is not None else list(range(W))
                 self.overlap_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
             self.overlap_plan = CommPlan(model.comm_buckets(), W, r, self.overlap_group)
-            if strategy in ("zero1", "zero2"):
+            if strategy in self.ZERO:
                 optimizer.set_shard(self.plan.owned_ranges())
                 f.master_consolidator = self.consolidate_master
                 self._build_fp32_exchange()
@@ -232,11 +256,14 @@ class TrainEngine:
             # identical initial parameters everywhere (rank 0 wins), like DDP's constructor broadcast
             dist.broadcast(f.master, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             f.sync_shadow(force=True)
-            if strategy == "zero2":
+            if strategy in self.GRAD_SHARDED:
                 self._setup_zero2()
-            self.shard_master = bool(shard_master) and strategy in ("zero1", "zero2")
+            # ZeRO-3 shards the 16-bit weights; the nn.Parameters then cannot stay views of a full fp32 master either
+            self.shard_master = (bool(shard_master) or strategy == "zero3") and strategy in self.ZERO
             if self.shard_master:
                 self._shard_master()
+            if strategy == "zero3":
+                self._setup_zero3()
         else:
             self.shard_master = False
 
@@ -318,7 +345,11 @@ class TrainEngine:
         for n in f.small_names():
             k = math.prod(f.alloc_shapes[n])
             f.small[f.small_offsets[n]:f.small_offsets[n] + k].copy_(full[f.offsets[n]:f.offsets[n] + k])
-        if f.device.type == "cuda":
+        if self.strategy == "zero3":  # only the owned 16-bit slices exist
+            for b, (lo, hi) in zip(self.plan.buckets, self.plan.owned_ranges()):
+                self._w16[self._w16_off[b]:self._w16_off[b] + hi - lo].copy_(full[lo:hi])
+            self._invalidate_weights()
+        elif f.device.type == "cuda":
             from . import kernels as K
 
             K.cast_f32_to_bf16(full, f.shadow)
@@ -378,6 +409,101 @@ class TrainEngine:
         self._gshard[off:off + own.numel()].add_(own)
         buf.zero_()
 
+    # ------------------------------------------------------------------ ZeRO-3: sharded 16-bit weights, gathered per bucket
+    def _setup_zero3(self) -> None:
+        """DeepSpeed stage 3 / FSDP full_shard (src/train.py:126-136,183-194): on top of the ZeRO-2 gradient handling and the sharded
+        fp32 master, the 16-bit compute copy is sharded too — each rank keeps the slices it owns (2 B/param/W, packed like the moments).
+        The module announces every bucket right before it reads it (forward: param_wait_hook, backward: param_bwd_hook); the engine
+        all-gathers that bucket into a transient buffer (ring of two per bucket size) and prefetches the next one of the same direction
+        on the side stream, so the gather of layer i+1 runs under the kernels of layer i. Per rank: 2 + 4 + 8 + 4 = 18 B/param/W
+        (weights, fp32 master, moments, gradient shard) + the transient buffers + the replicated fp32 1-D parameters."""
+        f = self.flat
+        dev, dtype = f.device, f.shadow.dtype
+        owned = self.plan.owned_ranges()
+        self._w16 = torch.empty(sum(hi - lo for lo, hi in owned), dtype=dtype, device=dev)
+        self._w16_off, acc = {}, 0
+        for b, (lo, hi) in zip(self.plan.buckets, owned):
+            self._w16_off[b] = acc
+            self._w16[acc:acc + hi - lo].copy_(f.shadow[lo:hi])
+            acc += hi - lo
+        by_size: dict[int, int] = {}
+        for s, e in self.plan.buckets:
+            by_size[e - s] = by_size.get(e - s, 0) + 1
+        self._wring = {n: [torch.empty(n, dtype=dtype, device=dev) for _ in range(2 if cnt > 1 else 1)] for n, cnt in by_size.items()}
+        self._wring_next = {n: 0 for n in by_size}
+        self._wres: dict[tuple[int, int], torch.Tensor] = {}      # bucket -> buffer the compute stream may read now
+        self._wflight: dict[tuple[int, int], tuple] = {}          # bucket -> (buffer, event of its gather | None)
+        bwd = [tuple(b) for b in self.model.comm_buckets()]       # head, layers L-1 .. 0, input embedding
+        self._w_fwd_order = list(reversed(bwd))
+        self._w_bwd_order = bwd[:-1]                              # the embedding's backward is a scatter-add: no weight read
+        f.drop_shadow(dict(self.model.named_parameters()))
+        f.weight_router = self._route_weight
+        self.model.param_wait_hook = self._need_weights_fwd
+        self.model.param_bwd_hook = self._need_weights_bwd
+
+    def zero3_transient_bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for ring in self._wring.values() for b in ring)
+
+    def _route_weight(self, name: str):
+        """FlatParams.wview*: (buffer, element offset) of the gathered 16-bit copy of `name`."""
+        b = self._name_bucket[name]
+        buf = self._wres.get(b)
+        if buf is None:
+            raise RuntimeError(f"ZeRO-3: the weights of {name!r} are not resident — the module read them outside its parameter hooks")
+        return buf, self.flat.offsets[name] - b[0]
+
+    def _fetch_weights(self, b: tuple[int, int]) -> None:
+        """Start the all-gather of bucket b into the next ring buffer of its size."""
+        n = b[1] - b[0]
+        ring = self._wring[n]
+        buf = ring[self._wring_next[n] % len(ring)]
+        self._wring_next[n] += 1
+        for d in (self._wres, self._wflight):  # whatever still claimed this buffer is gone once it is overwritten
+            for ob in [ob for ob, v in d.items() if (v if d is self._wres else v[0]) is buf]:
+                del d[ob]
+        off = self._w16_off[b]
+        own = self._w16[off:off + n // self.plan.W]
+        if self.comm_stream is None or not self.overlap:
+            self.plan.all_gather_buffer(buf, own)
+            self._wflight[b] = (buf, None)
+            return
+        # the side stream waits for the compute stream as of NOW: every kernel that read this buffer's previous contents was enqueued
+        # before its bucket was released (which happens before any fetch), and so was the cast that last wrote the 16-bit shard
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            self.overlap_plan.all_gather_buffer(buf, own)
+            done = torch.cuda.Event()
+            done.record()
+        self._wflight[b] = (buf, done)
+
+    def _need_weights(self, start: int, end: int, order: list) -> None:
+        b = (start, end)
+        if b not in self._wres:
+            if b not in self._wflight:
+                self._fetch_weights(b)
+            buf, ev = self._wflight.pop(b)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+            self._wres[b] = buf
+        for ob in [ob for ob in self._wres if ob != b]:  # every kernel of the previous buckets is already enqueued: release them
+            del self._wres[ob]
+        i = order.index(b) if b in order else -1
+        if 0 <= i < len(order) - 1 and order[i + 1] not in self._wflight:
+            self._fetch_weights(order[i + 1])
+
+    def _need_weights_fwd(self, start: int, end: int) -> None:
+        self._need_weights(start, end, self._w_fwd_order)
+
+    def _need_weights_bwd(self, start: int, end: int) -> None:
+        self._need_weights(start, end, self._w_bwd_order)
+
+    def _invalidate_weights(self) -> None:
+        """The 16-bit shard changed (optimizer step, load): gathered copies are stale."""
+        self._wres.clear()
+        self._wflight.clear()
+
     # ------------------------------------------------------------------ fwd + bwd of one micro-batch
     def _reduce_bucket(self, plan: CommPlan, b: tuple[int, int]) -> None:
         if self.strategy == "ddp":
@@ -387,7 +513,7 @@ class TrainEngine:
 
     def _on_grads_ready(self, start: int, end: int) -> None:
         b = self.plan.bucket_of(start, end)
-        if self.strategy == "zero2":
+        if self.strategy in self.GRAD_SHARDED:
             buf = self._active.pop(b, None)
             if buf is None:  # no gradient of this bucket was touched in this backward
                 return
@@ -422,7 +548,7 @@ class TrainEngine:
         """One micro-batch forward + backward with gradients ACCUMULATED; the loss is divided by the accumulation count
         before backward (HF:trainer.py:1925-1927). Returns the (undivided, unscaled) loss as a device scalar."""
         boundary = (self.micro + 1) % self.ga == 0
-        every = self.strategy == "zero2"  # gradient sharding reduces every micro-batch
+        every = self.strategy in self.GRAD_SHARDED  # gradient sharding reduces every micro-batch
         self.model.grad_ready_hook = self._on_grads_ready if (self.plan is not None and (boundary or every)) else None
         out = self.model(**inputs)
         loss = out["loss"]
@@ -436,7 +562,7 @@ class TrainEngine:
 
         f = self.flat
         sumsq = torch.zeros((), dtype=torch.float32, device=f.device)
-        if self.strategy == "zero2":
+        if self.strategy in self.GRAD_SHARDED:
             K.sumsq_(self._gshard, sumsq)
             self.plan.all_reduce_sum_scalar(sumsq)
         elif self.strategy == "zero1":
@@ -486,14 +612,14 @@ class TrainEngine:
         if overflow:
             scaler.skipped_steps += 1
             f.pending_grad_scale = None
-        elif self.strategy == "zero2":
+        elif self.strategy in self.GRAD_SHARDED:
             self.optimizer.step(grads=self._gshard, grads_packed=True)
         else:
             self.optimizer.step()
         if scaler is not None:
             scaler.update()
         marks.append(self._mark())
-        if self.strategy in ("zero1", "zero2") and not overflow:
+        if self.strategy in self.ZERO and not overflow:
             self._gather_params()
         marks.append(self._mark())
         if self.scheduler is not None and not overflow:
@@ -511,6 +637,16 @@ class TrainEngine:
         compute copy bucket by bucket in FORWARD order. With a side stream the gathers run there and the next forward waits
         per bucket (`_wait_params`), so they overlap zero_grad, the host gap between steps and the first layers."""
         f = self.flat
+        if self.strategy == "zero3":  # nothing to replicate: refresh the rank's 16-bit shard from its fp32 shard, and the fp32 1-D parameters
+            if f.device.type == "cuda":
+                from . import kernels as K
+
+                K.cast_f32_to_bf16(self.optimizer._p32, self._w16)
+            else:
+                self._w16.copy_(self.optimizer._p32)
+            self._exchange_fp32_params()
+            self._invalidate_weights()
+            return
         fwd_order = list(reversed(self.model.comm_buckets()))  # comm_buckets() is backward order
         side = self.comm_stream is not None and self.overlap_param_gather
         if not side:
@@ -573,7 +709,7 @@ class TrainEngine:
                      "dropout_step_seed": int(getattr(self.model, "_step_seed", 0)),
                      "loss_scaler": self.loss_scaler.state_dict() if self.loss_scaler is not None else None}
             (d / "trainer_state.json").write_text(json.dumps(state))
-        if self.strategy in ("zero1", "zero2"):
+        if self.strategy in self.ZERO:
             torch.save(self.optimizer.state_dict(), d / f"optimizer_rank{rank}.pt")
         elif rank == 0:
             torch.save(self.optimizer.state_dict(), d / "optimizer.pt")
@@ -596,7 +732,7 @@ class TrainEngine:
         self.model.load_state_dict(torch.load(d / "pytorch_model.bin", map_location="cpu"))
         self.flat.sync_shadow(force=True)
         self._param_events = {}
-        opt_file = d / (f"optimizer_rank{rank}.pt" if self.strategy in ("zero1", "zero2") else "optimizer.pt")
+        opt_file = d / (f"optimizer_rank{rank}.pt" if self.strategy in self.ZERO else "optimizer.pt")
         self.optimizer.load_state_dict(torch.load(opt_file, map_location="cpu"))
         if self.scheduler is not None and (d / "scheduler.pt").exists():
             self.scheduler.load_state_dict(torch.load(d / "scheduler.pt", map_location="cpu"))
@@ -613,7 +749,7 @@ class TrainEngine:
         f = self.flat
         if f.master is None:
             return  # sharded master: materialised on demand (flat.materialize_master)
-        if self.strategy in ("zero1", "zero2") and getattr(f, "master_stale", False):
+        if self.strategy in self.ZERO and getattr(f, "master_stale", False):
             self.sync_params()
             for b in self.plan.buckets:
                 self.plan.all_gather(f.master, b)

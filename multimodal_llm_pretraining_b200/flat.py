@@ -60,10 +60,50 @@ class FlatParams:
         self.small_offsets: dict[str, int] = {}
         self.master_materializer = None
         self.master_loader = None
+        # ZeRO-3 (engine.py, strategy "zero3"): the 16-bit compute copy is sharded as well (`shadow` is None; each rank keeps the slices
+        # it owns, 2 B/param/W); `weight_router(name)` returns the transient bucket buffer (and the offset inside it) into which the
+        # engine has all-gathered the bucket of `name` for the layer that is about to run.
+        self.weight_router = None
 
     @property
     def device(self) -> torch.device:
-        return (self.master if self.master is not None else self.shadow).device
+        for t in (self.master, self.shadow, self.small):
+            if t is not None:
+                return t.device
+        raise RuntimeError("empty parameter store")
+
+    # ---- 16-bit compute-copy views (through the router when the engine shards the weights)
+    def _wbuf(self, name: str) -> tuple[torch.Tensor, int]:
+        if self.weight_router is not None:
+            return self.weight_router(name)
+        return self.shadow, self.offsets[name]
+
+    def wview(self, name: str) -> torch.Tensor:
+        buf, o = self._wbuf(name)
+        s = self.shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def wview_alloc(self, name: str) -> torch.Tensor:
+        buf, o = self._wbuf(name)
+        s = self.alloc_shapes[name]
+        return buf[o:o + math.prod(s)].view(s)
+
+    def wview_span(self, first: str, shape: tuple[int, ...]) -> torch.Tensor:
+        buf, o = self._wbuf(first)
+        return buf[o:o + math.prod(shape)].view(shape)
+
+    def drop_shadow(self, params: dict[str, nn.Parameter]) -> None:
+        """Free the full 16-bit copy (ZeRO-3; the master must already be sharded). The nn.Parameters become empty placeholders that
+        keep their identity, names and `_b200_flat` record — like DeepSpeed stage 3, where `param.data` is an empty tensor between
+        uses and `ds_shape` / `ds_numel` carry the real geometry."""
+        if self.master is not None:
+            raise RuntimeError("drop_shadow: shard the fp32 master first (the parameters would still be views of it)")
+        dtype, dev = self.shadow.dtype, self.shadow.device
+        for name, p_ in params.items():
+            p_.ds_shape, p_.ds_numel = self.shapes[name], math.prod(self.shapes[name])  # type: ignore[attr-defined]
+            p_.grad = None
+            p_.data = torch.empty(0, dtype=dtype, device=dev)
+        self.shadow = None
 
     # ---- fp32 views of the parameters the kernels read in fp32 (1-D: biases, LayerNorm affine)
     def pview(self, name: str) -> torch.Tensor:

@@ -162,6 +162,14 @@ class _FlatModule(nn.Module):
         if self.param_wait_hook is not None:
             self.param_wait_hook(*rng)
 
+    # ZeRO-3 only: called in BACKWARD right before the weights of a bucket are read again (dgrad GEMMs, recomputation); None otherwise
+    param_bwd_hook = None
+    supports_weight_sharding = False  # True on modules whose backward announces its weight reads through `_need_bucket_bwd`
+
+    def _need_bucket_bwd(self, rng: tuple[int, int]) -> None:
+        if self.param_bwd_hook is not None:
+            self.param_bwd_hook(*rng)
+
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """Fused replacement for torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
         (src/benchmarking/utils.py:66-70): one sum-of-squares pass over the flat grad buffer; the clip coefficient stays
@@ -182,6 +190,7 @@ class _HeadGrad:
 
 class B200GPTNeoXForCausalLM(_FlatModule):
     supports_gradient_checkpointing = True
+    supports_weight_sharding = True
     main_input_name = "input_ids"
 
     def __init__(self, config):
@@ -274,7 +283,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         return self.embed_out
 
     def num_parameters(self, only_trainable: bool = False) -> int:
-        return sum(p.numel() for p in self.parameters())
+        return sum(p._b200_flat[2] for p in self.parameters())  # the store's record: valid while the tensors are sharded away too
 
     def load_hf_state_dict(self, sd: dict[str, torch.Tensor]) -> None:
         own = self.state_dict()
@@ -286,8 +295,8 @@ class B200GPTNeoXForCausalLM(_FlatModule):
                 v.copy_(sd[k].to(v.dtype))
 
     # ------------------------------------------------------------------ helpers
-    def _w(self, name: str) -> torch.Tensor:  # bf16 compute copy
-        return self.flat.view(self.flat.shadow, name)
+    def _w(self, name: str) -> torch.Tensor:  # bf16 compute copy (ZeRO-3: the bucket buffer the engine gathered it into)
+        return self.flat.wview(name)
 
     def _p(self, name: str) -> torch.Tensor:  # fp32 values the kernels read directly (LayerNorm affine, biases)
         return self.flat.pview(name)
@@ -407,6 +416,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
         B, S = ctx.B, ctx.S
         alpha = grad_out.reshape(1).to(torch.float32).contiguous()
         hook = self.grad_ready_hook
+        self._need_bucket_bwd(self._head_range())
         # LM head: dWout += alpha * dlogits^T xf ; dxf = alpha * dlogits Wout
         K.gemm(ctx.dlogits, ctx.xf, a_mn=True, b_mn=True, out=self._g("embed_out.weight"), accumulate=True, alpha=alpha)
         dxf = K.gemm(ctx.dlogits, self._w("embed_out.weight"), b_mn=True, alpha=alpha)
@@ -417,6 +427,7 @@ class B200GPTNeoXForCausalLM(_FlatModule):
             hook(*self.flat.range_of(["gpt_neox.final_layer_norm.weight", "gpt_neox.final_layer_norm.bias", "embed_out.weight"]))
         for i in reversed(range(self.L)):
             sv = ctx.saved_layers[i]
+            self._need_bucket_bwd(self._layer_ranges[i])
             if isinstance(sv, torch.Tensor):  # checkpointed: recompute this layer's activations
                 _, sv = self._layer_fwd(i, sv, B, S, keep=True)
             dx = self._layer_bwd(i, sv, dx, B, S)

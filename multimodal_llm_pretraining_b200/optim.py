@@ -84,7 +84,7 @@ class B200Adam(torch.optim.Optimizer):
             self._v = torch.zeros(acc, dtype=torch.float32, device=dev)
             if m_old is not None and m_old.numel() == acc:
                 self._m.copy_(m_old), self._v.copy_(v_old)
-        self._built_for = (dev, f.shadow.data_ptr(), tuple(ranges))
+        self._built_for = (dev, self._shadow_ptr(), tuple(ranges))
 
     def _ranges(self) -> list[tuple[int, int]]:
         if self._shard is None:
@@ -111,8 +111,12 @@ class B200Adam(torch.optim.Optimizer):
 
     def _ensure_built(self) -> None:
         f = self._flat
-        if self._built_for != (f.device, f.shadow.data_ptr(), tuple(self._ranges())):
+        if self._built_for != (f.device, self._shadow_ptr(), tuple(self._ranges())):
             self._build()
+
+    def _shadow_ptr(self) -> int:
+        sh = self._flat.shadow  # None under ZeRO-3: the engine casts the updated fp32 shard into its 16-bit shard itself
+        return 0 if sh is None else sh.data_ptr()
 
     def adopt_master_shard(self) -> torch.Tensor:
         """True ZeRO partition of the fp32 weights: copy the slices this rank owns out of the (still full) flat master into a packed

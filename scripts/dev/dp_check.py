@@ -169,6 +169,25 @@ def main():
         if rank == 0:
             print(f"{strategy} with a sharded fp32 master: == replicated-master {strategy} bit for bit {exact}, checkpoint round trip exact {restored}, "
                   f"step after resume equal {cont}, fp32 master per rank {opt._p32.numel() * 4 / 1e6:.1f} MB of {model.flat.numel * 4 / 1e6:.1f} -> {'OK' if good else 'FAIL'}", flush=True)
+    # ---- ZeRO-3 (strategy "zero3": 16-bit weights sharded too, gathered per bucket through the module's parameter hooks). Validated on
+    # CPU tensors over gloo (tests/test_host_schedule_cpu.py); it has NOT run on hardware yet, so this section is opt-in and does not gate the
+    # validated strategies: B200_DPCHECK_ZERO3=1. Same arithmetic as ZeRO-2 -> must equal it bit for bit.
+    if os.environ.get("B200_DPCHECK_ZERO3"):
+        for kw in ({}, {"overlap": False}):
+            model = build(cfg, dev)
+            opt = B200Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.95))
+            eng = TrainEngine(model, opt, None, max_grad_norm=1.0, gradient_accumulation_steps=ga, strategy="zero3", **kw)
+            for s in range(steps):
+                for m in range(ga):
+                    ids = data[s, m, rank].to(dev)
+                    eng.manual_training_step({"input_ids": ids, "labels": ids})
+                eng.manual_optimization_step()
+            full = model.flat.materialize_master()
+            exact = torch.equal(full, finals["zero2"])
+            ok = ok and exact
+            if rank == 0:
+                print(f"zero3{kw or ''}: == zero2 bit for bit {exact}; 16-bit weights per rank {eng._w16.numel() * 2 / 1e6:.1f} MB of {model.flat.numel * 2 / 1e6:.1f}, "
+                      f"transient gather buffers {eng.zero3_transient_bytes() / 1e6:.1f} MB -> {'OK' if exact else 'FAIL'}", flush=True)
     # ---- RoBERTa (tied decoder, padded vocabulary, both dropouts on): the same bit-for-bit requirement
     from multimodal_llm_pretraining_b200.modeling_roberta import B200RobertaForMaskedLM
     from multimodal_llm_pretraining_b200.models.configs import roberta_large_config_dict
