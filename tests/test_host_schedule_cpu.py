@@ -424,3 +424,26 @@ def test_real_modules_through_the_engine_world2(tmp_path, kind):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_torch_optimizer_interop_recasts_the_compute_copy(K, gold):
+    """A foreign optimizer (the reference's naive path hands out torch.optim.Adam) edits the fp32 master through torch: the version
+    counters move, the next forward re-casts the 16-bit copy; zero_grad(set_to_none=True) drops the gradient views and the module
+    re-attaches them."""
+    m = _neox(gold)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    ids = gold["batches"][0]
+    l0 = m(input_ids=ids, labels=ids).loss
+    l0.backward()
+    before = m.flat.shadow.clone()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    assert next(m.parameters()).grad is None
+    assert torch.equal(m.flat.shadow, before)                       # not yet re-cast ...
+    l1 = m(input_ids=ids, labels=ids).loss
+    assert torch.equal(m.flat.shadow, m.flat.master.to(m.flat.shadow.dtype)) and not torch.equal(m.flat.shadow, before)  # ... now it is
+    assert l1.item() < l0.item()
+    l1.backward()
+    p = next(m.parameters())
+    assert p.grad is not None and p.grad.data_ptr() == m.flat.view(m.flat.grad, "gpt_neox.embed_in.weight").data_ptr()
+    assert float(m.flat.grad.abs().max()) > 0
