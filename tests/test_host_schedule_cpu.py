@@ -271,6 +271,36 @@ def _noise_mask(m):
     return keep
 
 
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+
+class _FakeStream:
+    def wait_event(self, ev):
+        assert isinstance(ev, _FakeEvent)
+
+    def wait_stream(self, st):
+        assert isinstance(st, _FakeStream)
+
+
+def _fake_side_stream(eng):
+    """Drive the engine's OVERLAP branches (side stream + events: the default on a GPU) on CPU tensors: streams and events become no-ops,
+    so every collective runs at the point where it is enqueued — program order, which is one of the orders the real streams allow. What
+    this checks is the bookkeeping of those branches (ring buffers, in-flight gathers, per-bucket events); the ordering itself is a
+    property of the CUDA streams and is checked on hardware by scripts/dev/dp_check.py."""
+    import contextlib
+
+    torch.cuda.Event = _FakeEvent
+    torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+    torch.cuda.stream = lambda st: contextlib.nullcontext()
+    eng.comm_stream = _FakeStream()
+    assert eng.overlap and eng.overlap_plan is not None
+
+
 def _dp_worker(rank, world, port, q, tmpdir, kind):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -295,6 +325,7 @@ def _dp_worker(rank, world, port, q, tmpdir, kind):
             if ckpt:
                 model.gradient_checkpointing_enable()
             opt = Opt(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+            side = kw.pop("side", False)
             if strategy == "none":  # one process, the whole global batch: micro-batches of every rank in turn
                 eng = TrainEngine(model, opt, None, max_grad_norm=0.5, gradient_accumulation_steps=ga * world, strategy="none", **kw)
                 for s in range(steps):
@@ -304,6 +335,8 @@ def _dp_worker(rank, world, port, q, tmpdir, kind):
                     assert eng.manual_optimization_step()
             else:
                 eng = TrainEngine(model, opt, None, max_grad_norm=0.5, gradient_accumulation_steps=ga, strategy=strategy, **kw)
+                if side:
+                    _fake_side_stream(eng)
                 for s in range(steps):
                     for m in range(ga):
                         eng.manual_training_step({"input_ids": data[s, m, rank], "labels": data[s, m, rank]})
@@ -393,6 +426,9 @@ def _dp_worker(rank, world, port, q, tmpdir, kind):
         else:
             with pytest.raises(NotImplementedError, match="zero3"):
                 train("zero3")
+        # the overlap branches (side stream, events, in-flight gathers, ring reuse) with no-op streams: same results. LAST in this
+        # worker: torch.cuda.Event / stream / current_stream stay patched afterwards
+        tail = [("ddp", {}), ("zero1", {}), ("zero2", {}), ("zero1", {"shard_master": True})] + ([("zero3", {}), ("zero3", {"ckpt": True})] if kind == "neox" else [])
         # activation checkpointing recomputes the same statements: bit-identical to the plain run of the same strategy
         _, _, _, full = train("zero1", ckpt=True)
         assert torch.equal(full, finals["zero1"])
@@ -403,6 +439,11 @@ def _dp_worker(rank, world, port, q, tmpdir, kind):
         assert abs(float(eng.last_grad_norm) - norms["zero1"]) < 2e-2 * norms["zero1"], (float(eng.last_grad_norm), norms["zero1"])
         # ... and the update against the bf16 run of the same strategy: two roundings (8 vs 11 significant bits) of one computation
         assert diff(full, finals["zero1"]) < 0.15, diff(full, finals["zero1"])
+        for strategy, kw in tail:
+            _, eng, _, full = train(strategy, side=True, **kw)
+            assert torch.equal(full, finals["zero2" if strategy == "zero3" else strategy]), ("side stream", strategy, kw)
+            if strategy in ("zero1",) and not kw:
+                assert eng._param_events, "the per-bucket gather events of the side-stream branch were not recorded"
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
