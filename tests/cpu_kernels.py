@@ -104,12 +104,23 @@ def roberta_position_ids(ids, pad_id: int):
     return torch.cumsum(mask, 1) * mask + pad_id
 
 
+def _keep_mask(seed: int, shape, p: float):
+    """STAND-IN for the kernels' counter-based masks: like them a pure function of (seed, element position), so that the host logic
+    around them (which seed each site uses, that backward and recomputation reuse the forward's seed, that every step draws new masks)
+    behaves the same; NOT the kernels' hash — the masks themselves are checked on the GPU (test_attention_gpu.py, test_roberta_gpu.py)."""
+    g = torch.Generator().manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
+    return torch.rand(shape, generator=g) >= p
+
+
 def dropout(x, p: float, seed: int, residual=None, out=None):
+    y = x.float()
     if p > 0.0:
-        raise NotImplementedError("the CPU statement covers dropout 0 only (masks are checked on the GPU against the kernel's own hash)")
-    y = x if residual is None else (x.float() + residual.float()).to(x.dtype)
+        y = y * _keep_mask(seed, x.shape, p) / (1.0 - p)
+    if residual is not None:
+        y = y + residual.float()
+    y = y.to(x.dtype)
     if out is None:
-        return y.clone()
+        return y
     out.copy_(y)
     return out
 
@@ -165,8 +176,9 @@ def gemm(A, B, *, a_mn=False, b_mn=False, out=None, out_dtype=None, accumulate=F
         acc = acc * _dgelu(dgelu_in.float())
         if colsum_out is not None:
             colsum_out += acc.sum(0)
-    if dropout_p > 0.0:
-        raise NotImplementedError("the CPU statement covers dropout 0 only")
+    if dropout_p > 0.0:  # the epilogue's mask is K.dropout's: the same function of (seed, output element)
+        assert residual is not None
+        acc = acc * _keep_mask(dropout_seed, acc.shape, dropout_p) / (1.0 - dropout_p)
     if residual is not None:
         acc = acc + residual.float()
     if out is None:
@@ -190,27 +202,29 @@ def _scores(q, k, causal, scale):
 
 
 def attention_fwd(q, k, v, causal, scale=None, dropout_p: float = 0.0, dropout_seed: int = 0):
-    if dropout_p > 0.0:
-        raise NotImplementedError("the CPU statement covers dropout 0 only")
     D = q.shape[3]
     scale = D ** -0.5 if scale is None else scale
     s = _scores(q, k, causal, scale)
     lse = torch.logsumexp(s, -1)                                  # [B, H, S]
     p = torch.exp(s - lse[..., None])
+    if dropout_p > 0.0:  # probabilities dropped after the softmax; lse stays that of the undropped scores
+        p = p * _keep_mask(dropout_seed, p.shape, dropout_p) / (1.0 - dropout_p)
     o = torch.einsum("bhqk,bkhd->bqhd", p, v.float()).to(q.dtype).contiguous()
     return o, lse.contiguous()
 
 
 def attention_bwd(q, k, v, o, lse, d_o, dq, dk, dv, causal, scale=None, dropout_p: float = 0.0, dropout_seed: int = 0):
-    if dropout_p > 0.0:
-        raise NotImplementedError("the CPU statement covers dropout 0 only")
     D = q.shape[3]
     scale = D ** -0.5 if scale is None else scale
     p = torch.exp(_scores(q, k, causal, scale) - lse[..., None])
     do = d_o.float()
-    dv.copy_(torch.einsum("bhqk,bqhd->bkhd", p, do).to(dv.dtype))
     dp = torch.einsum("bqhd,bkhd->bhqk", do, v.float())
-    delta = (do * o.float()).sum(-1).permute(0, 2, 1)             # [B, H, S]
+    pd = p
+    if dropout_p > 0.0:
+        m = _keep_mask(dropout_seed, p.shape, dropout_p) / (1.0 - dropout_p)
+        pd, dp = p * m, dp * m
+    dv.copy_(torch.einsum("bhqk,bqhd->bkhd", pd, do).to(dv.dtype))
+    delta = (do * o.float()).sum(-1).permute(0, 2, 1)             # [B, H, S]; = sum_k p * dp(masked) for the dropped forward too
     ds = p * (dp - delta[..., None]) * scale
     dq.copy_(torch.einsum("bhqk,bkhd->bqhd", ds, k.float()).to(dq.dtype))
     dk.copy_(torch.einsum("bhqk,bqhd->bkhd", ds, q.float()).to(dk.dtype))

@@ -488,3 +488,58 @@ def test_torch_optimizer_interop_recasts_the_compute_copy(K, gold):
     p = next(m.parameters())
     assert p.grad is not None and p.grad.data_ptr() == m.flat.view(m.flat.grad, "gpt_neox.embed_in.weight").data_ptr()
     assert float(m.flat.grad.abs().max()) > 0
+
+
+def test_roberta_dropout_seed_plumbing(K, gold_r):
+    """Both dropouts on (the roberta-large configuration). The masks are functions of (step seed, site, element): backward and
+    activation recomputation must regenerate the forward's masks, every training forward must draw new ones, eval must draw none, and
+    the analytic gradient must agree with a finite difference of the SAME masked function (a backward that used other masks would not)."""
+    cfg = dict(gold_r["cfg"], hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    ids = gold_r["batches"][0]
+
+    def build():
+        m = CpuRoberta(SimpleNamespace(**cfg))
+        m.load_hf_state_dict(gold_r["state_dict"])
+        return m.train()
+
+    m = build()
+    l1 = m(input_ids=ids, labels=ids)["loss"]
+    l1.backward()
+    g_plain = m.flat.grad.clone()
+    l2 = m(input_ids=ids, labels=ids)["loss"]
+    assert m._step_seed == 2 and l1.item() != l2.item()            # same batch, same weights, new masks
+    m.eval()
+    e1, e2 = m(input_ids=ids, labels=ids)["loss"].item(), m(input_ids=ids, labels=ids)["loss"].item()
+    assert e1 == e2 and m._step_seed == 2                             # no dropout, no seed consumed
+    # recomputation in backward regenerates the same masks: bit-identical gradients for the same step seed
+    mc = build()
+    mc.gradient_checkpointing_enable()
+    lc = mc(input_ids=ids, labels=ids)["loss"]
+    assert lc.item() == l1.item()
+    lc.backward()
+    assert torch.equal(mc.flat.grad, g_plain)
+    # a forward of ANOTHER step between forward and backward must not change the masks the backward uses
+    mi = build()
+    la = mi(input_ids=ids, labels=ids)["loss"]
+    mi(input_ids=ids, labels=ids)["loss"]                            # bumps the step seed, graph discarded
+    la.backward()
+    assert torch.equal(mi.flat.grad, g_plain)
+    # directional finite difference of the masked loss (step seed pinned) against the analytic gradient
+    name = "roberta.encoder.layer.0.output.dense.bias"                 # fp32 parameter read directly by the kernels: no 16-bit rounding of the step
+    mf = build()
+    p = dict(mf.named_parameters())[name]
+    d = torch.randn(p.shape, generator=torch.Generator().manual_seed(0))
+    d = d / d.norm()
+
+    def loss_at(eps):
+        mf._step_seed = 0
+        with torch.no_grad():
+            p.add_(eps * d)
+        out = mf(input_ids=ids, labels=ids)["loss"].item()
+        with torch.no_grad():
+            p.sub_(eps * d)
+        return out
+
+    fd = (loss_at(0.05) - loss_at(-0.05)) / 0.1
+    an = float((mf.flat.view(g_plain, name) * d).sum())
+    assert abs(fd - an) <= 0.15 * abs(an) + 2e-3, (fd, an)
