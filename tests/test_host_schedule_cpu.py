@@ -5,6 +5,7 @@ everything ABOVE the kernels: which tensor feeds which GEMM in which layout, whe
 optimizer touches, what the engine exchanges — against the HF golden fixtures and against each other across strategies (gloo,
 world_size 2). The kernels themselves are checked on the GPU (`-m gpu`); the product's own CPU guards stay in place (the test
 subclasses override `_require_cuda`, nothing else)."""
+import math
 import os
 import sys
 from pathlib import Path
@@ -543,3 +544,44 @@ def test_roberta_dropout_seed_plumbing(K, gold_r):
     fd = (loss_at(0.05) - loss_at(-0.05)) / 0.1
     an = float((mf.flat.view(g_plain, name) * d).sum())
     assert abs(fd - an) <= 0.15 * abs(an) + 2e-3, (fd, an)
+
+
+def test_reference_surface_to_engine_on_cpu(K, monkeypatch):
+    """TrainingConfig -> TrainingClass.build_trainer -> ManualTrainer (optimizer class hand-off, HF's two parameter groups, scheduler from
+    the TrainingArguments dict) -> the reference's two harness calls, on a tiny module."""
+    from multimodal_llm_pretraining_b200.benchmarking.utils import ManualTrainer
+    from multimodal_llm_pretraining_b200.config import TrainingConfig
+
+    monkeypatch.setattr(B200Adam, "_require_cuda", lambda self: None)
+    config = TrainingConfig(1, 1, "b200", "pythia-70m", free_lunch=True)
+    tc = config.training_class(num_training_steps=4, micro_batch_size=2, gradient_accumulation_steps=2, bf16=True, fp16=False)
+    assert tc.is_valid() and tc.runs_on_b200_engine()
+    mc = config.model_class()
+    assert mc.optimizer is torch.optim.Adam                       # the registry hands out the reference's own class ...
+    model = _build("neox")
+    ds = mc.load_dummy_dataset(num_samples=16, seed=0)
+    ds.input_ids %= TINY["vocab_size"]
+    ds.labels %= TINY["vocab_size"]
+    ds.input_ids, ds.labels = ds.input_ids[:, :33], ds.labels[:, :33]
+    trainer = tc.build_trainer(model, ds, hf_trainer_kwargs_overrides={"device": torch.device("cpu")})
+    assert isinstance(trainer, ManualTrainer) and type(trainer.optimizer) is B200Adam   # ... the trainer swaps in the fused twin
+    assert trainer.engine.strategy == "none" and trainer.engine.ga == 2
+    groups = trainer.optimizer.param_groups
+    assert len(groups) == 2 and all(p.dim() >= 2 for p in groups[0]["params"]) and all(p.dim() < 2 for p in groups[1]["params"])
+    assert all(g["weight_decay"] == 0.0 for g in groups)            # TrainingArguments.weight_decay = 0 overrides the model class's kwarg
+    assert groups[0]["betas"] == tuple(mc.optimizer_kwargs["betas"]) and groups[0]["eps"] == mc.optimizer_kwargs["eps"]
+    it = iter(trainer.get_train_dataloader())
+    lrs, losses = [], []
+    before = model.flat.master.clone()
+    for _ in range(3):
+        for _ in range(2):
+            losses.append(float(trainer.manual_training_step(trainer.model, next(it))))
+        lrs.append(groups[0]["lr"])
+        assert trainer.manual_optimization_step(trainer.model)
+    assert trainer.optimizer._step == 3 and trainer.lr_scheduler.last_epoch == 3
+    assert len(set(lrs)) > 1, "the schedule of the TrainingArguments dict must drive the fused optimizer's lr"
+    assert all(math.isfinite(x) for x in losses) and not torch.equal(model.flat.master, before)
+    assert float(model.flat.grad.abs().max()) == 0.0                 # zero_grad at the end of the optimization step
+    # a stock HF-style module (no flat store) is refused with a message, not trained on a silent fallback
+    with pytest.raises(NotImplementedError, match="B200 modules"):
+        tc.build_trainer(torch.nn.Linear(4, 4), ds, hf_trainer_kwargs_overrides={"device": torch.device("cpu")})
