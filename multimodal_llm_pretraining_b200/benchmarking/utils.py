@@ -7,6 +7,7 @@ the pieces of HF Trainer state the harness reads (`args`, `model_wrapped`, `opti
 `get_train_dataloader()`)."""
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Any
 
@@ -29,8 +30,11 @@ def strategy_for(world_size: int, zero_stage: str = "0", fsdp_sharding: str = "n
         return "zero2"
     if zero_stage == "0" and fsdp_sharding == "no_shard":
         return "ddp"
+    if (zero_stage == "3" or fsdp_sharding == "full_shard") and os.environ.get("B200_EXPERIMENTAL_ZERO3"):
+        return "zero3"  # engine.py: validated over gloo on CPU tensors only (tests/test_host_schedule_cpu.py), hence opt-in
     raise NotImplementedError(f"zero_stage={zero_stage!r} fsdp_sharding={fsdp_sharding!r}: parameter sharding (ZeRO-3 / FSDP full_shard) "
-                              "and offload are outside this build's scope (SURVEY.md §2.3, §8f rank 3)")
+                              "is built in the engine (strategy 'zero3') but has not run on hardware yet — set B200_EXPERIMENTAL_ZERO3=1 "
+                              "to select it; hybrid sharding and offload are outside this build's scope (SURVEY.md §2.3, §8f rank 3)")
 
 
 class ManualTrainer:
