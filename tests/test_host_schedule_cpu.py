@@ -605,3 +605,32 @@ def test_neox_opt_in_fused_bias_gradient_schedule(K, gold, monkeypatch):
             assert rel(a, b) <= 1e-2, (n, rel(a, b))   # column sums of the fp32 accumulator instead of the rounded dh1
         else:
             assert torch.equal(a, b), n
+
+
+@pytest.mark.parametrize("nh,h,pct", [(2, 256, 0.25), (1, 256, 0.25), (4, 320, 0.25), (2, 128, 1.0)])  # head_dim 128, 256, 80 (rot 20), full rotary
+def test_neox_schedule_vs_fp32_oracle_other_head_shapes(K, nh, h, pct):
+    """The same check against the fp32 CPU oracle for the other Pythia head shapes: rotary tables / packed-qkv views / strides are host
+    logic that depends on (heads, head_dim, rotary fraction)."""
+    from oracle import neox_oracle as O
+
+    cfg = dict(vocab_size=512, hidden_size=h, num_hidden_layers=2, num_attention_heads=nh, intermediate_size=4 * h, rotary_pct=pct,
+               rotary_emb_base=10000, layer_norm_eps=1e-5)
+    m = CpuNeoX(SimpleNamespace(**cfg))
+    m.reset_parameters(torch.Generator().manual_seed(nh))
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(nh + 1)
+        for n, p in m.named_parameters():
+            if n.endswith(".bias"):
+                p.normal_(0, 0.02, generator=g)
+    m.train()
+    ids = torch.randint(0, 512, (2, 65), generator=torch.Generator().manual_seed(5))
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    ref_loss, ref_grads = O.neox_loss_and_grads(P, ids, ids, cfg)
+    loss = m(input_ids=ids, labels=ids).loss
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * ref_loss.item()
+    for n, p in m.named_parameters():
+        a, b = p.grad, ref_grads[n]
+        if n.endswith("query_key_value.bias"):
+            a, b = a.view(nh, 3, -1)[:, [0, 2]], b.view(nh, 3, -1)[:, [0, 2]]
+        assert rel(a, b) <= 2e-2, (n, rel(a, b))
