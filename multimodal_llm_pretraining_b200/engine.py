@@ -31,7 +31,7 @@ every rank runs independent micro-batches; the only exchange is per optimizer st
                      AND the 16-bit compute copy exist only as the slices a rank owns (18 B/param/W with moments and the gradient
                      shard); the module announces each bucket right before it reads it, in forward and again in backward, and the
                      engine all-gathers it into a transient buffer (ring of two per bucket size) while prefetching the next one of
-                     that direction on the side stream. GPT-NeoX modules only. Exercised with the real module over gloo on CPU
+                     that direction on the side stream. Exercised with the real module over gloo on CPU
                      (tests/test_host_schedule_cpu.py: equal to ZeRO-2 bit for bit, checkpoint round trip, activation
                      checkpointing); NOT yet run on hardware, hence not selectable through the reference-facing `sharding=zero_3`.
 
@@ -436,6 +436,8 @@ class TrainEngine:
         bwd = [tuple(b) for b in self.model.comm_buckets()]       # head, layers L-1 .. 0, input embedding
         self._w_fwd_order = list(reversed(bwd))
         self._w_bwd_order = bwd[:-1]                              # the embedding's backward is a scatter-add: no weight read
+        deps = getattr(self.model, "weight_bucket_deps", None)    # buckets read together (RoBERTa: head + the tied decoder matrix)
+        self._w_deps = {tuple(k): [tuple(x) for x in v] for k, v in (deps() if deps else {}).items()}
         f.drop_shadow(dict(self.model.named_parameters()))
         f.weight_router = self._route_weight
         self.model.param_wait_hook = self._need_weights_fwd
@@ -480,17 +482,19 @@ class TrainEngine:
 
     def _need_weights(self, start: int, end: int, order: list) -> None:
         b = (start, end)
-        if b not in self._wres:
-            if b not in self._wflight:
-                self._fetch_weights(b)
-            buf, ev = self._wflight.pop(b)
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
-            self._wres[b] = buf
-        for ob in [ob for ob in self._wres if ob != b]:  # every kernel of the previous buckets is already enqueued: release them
+        need = [b] + self._w_deps.get(b, [])
+        for ob in [ob for ob in self._wres if ob not in need]:  # every kernel of the previous buckets is already enqueued: release them
             del self._wres[ob]
+        for nb in need:
+            if nb not in self._wres:
+                if nb not in self._wflight:
+                    self._fetch_weights(nb)
+                buf, ev = self._wflight.pop(nb)
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                self._wres[nb] = buf
         i = order.index(b) if b in order else -1
-        if 0 <= i < len(order) - 1 and order[i + 1] not in self._wflight:
+        if 0 <= i < len(order) - 1 and order[i + 1] not in self._wflight and order[i + 1] not in self._wres:
             self._fetch_weights(order[i + 1])
 
     def _need_weights_fwd(self, start: int, end: int) -> None:

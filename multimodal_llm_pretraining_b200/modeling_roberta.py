@@ -211,11 +211,11 @@ class B200RobertaForMaskedLM(_FlatModule):
         return self.lm_head.decoder
 
     def num_parameters(self, only_trainable: bool = False) -> int:
-        return sum(p.numel() for p in self.parameters())
+        return sum(p._b200_flat[2] for p in self.parameters())
 
     # ------------------------------------------------------------------ helpers
     def _w(self, name):
-        return self.flat.view(self.flat.shadow, name)
+        return self.flat.wview(name)
 
     def _p(self, name):
         return self.flat.pview(name)
@@ -224,7 +224,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         return self.flat.gview(name)
 
     def _qkv_w(self, p):  # [3h, h] bf16: query | key | value rows
-        return self.flat.view_span(self.flat.shadow, f"{p}.attention.self.query.weight", (3 * self.h, self.h))
+        return self.flat.wview_span(f"{p}.attention.self.query.weight", (3 * self.h, self.h))
 
     def _qkv_b(self, p, buf):
         return self.flat.view_span(buf, f"{p}.attention.self.query.bias", (3 * self.h,))
@@ -241,6 +241,14 @@ class B200RobertaForMaskedLM(_FlatModule):
 
     def _seed(self, site: int) -> int:
         return (self._cur_seed * 1_000_003 + site) & 0xFFFFFFFFFFFF
+
+    supports_weight_sharding = True
+
+    def weight_bucket_deps(self) -> dict[tuple[int, int], list[tuple[int, int]]]:
+        """ZeRO-3: buckets that must be resident TOGETHER with a bucket — the head reads the tied decoder matrix, which lives in the
+        embeddings bucket."""
+        b = self.comm_buckets()
+        return {tuple(b[0]): [tuple(b[-1])]}
 
     def comm_buckets(self) -> list[tuple[int, int]]:
         """Flat-grad ranges in backward completion order: head, layers L-1..0, embeddings (the tied decoder gradient is
@@ -328,7 +336,7 @@ class B200RobertaForMaskedLM(_FlatModule):
         d_pre = torch.empty_like(x) if keep else None
         d = K.gemm(x, self._w("lm_head.dense.weight"), bias=self._p("lm_head.dense.bias"), gelu=True, aux_out=d_pre)
         n, _, mean, rstd = K.layernorm_fwd(d, self._p("lm_head.layer_norm.weight"), self._p("lm_head.layer_norm.bias"), self.eps)
-        w_dec = self.flat.view_alloc(self.flat.shadow, "roberta.embeddings.word_embeddings.weight")  # [Vp, h], zero padding
+        w_dec = self.flat.wview_alloc("roberta.embeddings.word_embeddings.weight")  # [Vp, h], zero padding
         b_dec = self.flat.pview_alloc("lm_head.bias")
         logits = K.gemm(n, w_dec, bias=b_dec)  # [T, Vp] bf16
         return logits, (x, d_pre, d, n, mean, rstd)
@@ -356,13 +364,15 @@ class B200RobertaForMaskedLM(_FlatModule):
         self._cur_seed = ctx.seed  # backward recomputes the dropout masks of ITS forward
         alpha = grad_out.reshape(1).to(torch.float32).contiguous()
         hook = self.grad_ready_hook
+        buckets = self.comm_buckets()
+        self._need_bucket_bwd(buckets[0])  # ZeRO-3: head (+ the tied decoder matrix, see weight_bucket_deps)
         x, d_pre, d, n, mean, rstd = ctx.head
         dl = ctx.dlogits
         g_dec = f.gview_alloc("roberta.embeddings.word_embeddings.weight")
         K.gemm(dl, n, a_mn=True, b_mn=True, out=g_dec, accumulate=True, alpha=alpha)
         # decoder bias grad = alpha * colsum(dlogits)
         K.colsum_(dl, f.gview_alloc("lm_head.bias"), scale=alpha)
-        dn = K.gemm(dl, f.view_alloc(f.shadow, "roberta.embeddings.word_embeddings.weight"), b_mn=True, alpha=alpha)
+        dn = K.gemm(dl, f.wview_alloc("roberta.embeddings.word_embeddings.weight"), b_mn=True, alpha=alpha)
         ctx.dlogits = None
         dd = K.layernorm_bwd(d, mean, rstd, self._p("lm_head.layer_norm.weight"), dn,
                              self._g("lm_head.layer_norm.weight"), self._g("lm_head.layer_norm.bias"))
@@ -370,11 +380,11 @@ class B200RobertaForMaskedLM(_FlatModule):
         K.gemm(dd_pre, x, a_mn=True, b_mn=True, out=self._g("lm_head.dense.weight"), accumulate=True)
         K.colsum_(dd_pre, self._g("lm_head.dense.bias"))
         dx = K.gemm(dd_pre, self._w("lm_head.dense.weight"), b_mn=True)
-        buckets = self.comm_buckets()
         if hook:
             hook(*buckets[0])
         for i in reversed(range(self.L)):
             sv = ctx.layers[i]
+            self._need_bucket_bwd(buckets[1 + (self.L - 1 - i)])
             if isinstance(sv, torch.Tensor):  # checkpointed: recompute this layer's activations (same masks: seed restored above)
                 _, sv = self._layer_fwd(i, sv, B, S, True)
             dx = self._layer_bwd(i, sv, dx, B, S, True)

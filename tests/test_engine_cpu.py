@@ -514,3 +514,14 @@ def test_fp16_overflow_on_one_rank_skips_the_step_everywhere_world2(tmp_path):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_zero3_refuses_modules_without_backward_weight_hooks():
+    """ZeRO-3 gathers weights per bucket on the module's announcement; a module that does not announce its backward reads would read
+    released buffers, so the engine refuses it up front."""
+    from multimodal_llm_pretraining_b200.engine import TrainEngine
+
+    Toy, ToyAdam = _toy_classes()
+    model = Toy()
+    with pytest.raises(NotImplementedError, match="zero3"):
+        TrainEngine(model, ToyAdam(model.flat), None, strategy="zero3")
