@@ -5,12 +5,14 @@ reference shows the expected output), including the FSDP option list and the Dee
 `scripts/to_training_arguments.py` keeps emitting the same artefact. `build_trainer()` returns the B200 step engine
 (multimodal_llm_pretraining_b200.benchmarking.utils.ManualTrainer) instead of transformers.Trainer. What runs on this
 build: no sharding (DDP), zero_stage "1", zero_stage "2" / fsdp "shard_grad_op" (gradient sharding), bf16 or fp16 (+ dynamic
-loss scaling), with or without activation checkpointing; parameter sharding (ZeRO-3, FSDP full_shard / hybrid) and offload
-are out of scope.
+loss scaling), with or without activation checkpointing. Parameter sharding (zero_stage "3" / fsdp "full_shard") exists in the engine
+(strategy "zero3") but has only been validated over gloo on CPU tensors, so it is selectable here only with
+B200_EXPERIMENTAL_ZERO3=1; hybrid sharding and offload are out of scope.
 """
 from __future__ import annotations
 
 import gc
+import os
 from dataclasses import dataclass, field
 from typing import Any, Literal
 
@@ -74,8 +76,13 @@ class TrainingClass:
         )
 
     def runs_on_b200_engine(self) -> bool:
-        return (self.fsdp_sharding in ("no_shard", "shard_grad_op") and self.zero_stage in ("0", "1", "2")
-                and not self.zero_offload_optimizer and not self.zero_offload_params and not self.fsdp_offload)
+        if self.zero_offload_optimizer or self.zero_offload_params or self.fsdp_offload:
+            return False
+        if self.fsdp_sharding in ("no_shard", "shard_grad_op") and self.zero_stage in ("0", "1", "2"):
+            return True
+        # parameter sharding: engine strategy "zero3", not yet run on hardware -> opt-in (benchmarking/utils.py: strategy_for)
+        return bool(os.environ.get("B200_EXPERIMENTAL_ZERO3")) and (
+            (self.zero_stage == "3" and self.fsdp_sharding == "no_shard") or (self.fsdp_sharding == "full_shard" and self.zero_stage == "0"))
 
     def build_trainer(self, model: nn.Module, train_dataset: Dataset, hf_training_args_overrides: dict[str, Any] = {},
                       hf_trainer_kwargs_overrides: dict[str, Any] = {}):
