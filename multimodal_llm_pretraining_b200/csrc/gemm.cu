@@ -782,7 +782,11 @@ extern "C" int b200_gemm_bf16(const b200_gemm_args* a, b200_stream_t stream) {
     B200_REQUIRE(!a->aux_out || aligned16(a->aux_out), "gemm: aux_out must be 16B aligned");
     GemmParams p;
     fill_params(a, p);
+#ifdef B200_PERF_TRIAGE  // bits 0/1 skip epilogue work and give WRONG results: only in a library built for profiling (-DB200_PERF_TRIAGE)
     static const int dbg = getenv("B200_GEMM_DEBUG") ? atoi(getenv("B200_GEMM_DEBUG")) : 0;
+#else
+    constexpr int dbg = 0;
+#endif
     static const int force_cg = getenv("B200_GEMM_CG") ? atoi(getenv("B200_GEMM_CG")) : 0;  // perf triage: 1 = single-CTA engine
     p.debug = dbg;
     p.tma_store = (!a->c_fp32 && !a->accumulate && !(dbg & 64)) ? 1 : 0;
