@@ -136,10 +136,10 @@ class CommPlan:
 
     def owned_mask(self, idx: torch.Tensor) -> torch.Tensor:
         """bool mask over the flat-buffer element indices `idx`: True where this rank owns the element."""
-        own = torch.zeros(int(idx.max().item()) + 1 if idx.numel() else 0, dtype=torch.bool)
-        for lo, hi in self.owned_ranges():
-            own[lo:hi] = True
-        return own[idx.cpu()].to(idx.device)
+        own = torch.zeros(idx.numel(), dtype=torch.bool, device=idx.device)
+        for lo, hi in self.owned_ranges():  # one comparison pair per bucket over the (few) indices: no flat-buffer-sized temporary
+            own |= (idx >= lo) & (idx < hi)
+        return own
 
     def exchange_owned(self, flat: torch.Tensor, idx: torch.Tensor, own: torch.Tensor) -> None:
         """flat[idx] <- the owning rank's value, on every rank: owners contribute their elements to one packed buffer, the
