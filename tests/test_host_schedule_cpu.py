@@ -437,6 +437,10 @@ def _dp_worker(rank, world, port, q, tmpdir, kind):
         assert abs(float(eng.last_grad_norm) - norms["zero1"]) < 2e-2 * norms["zero1"], (float(eng.last_grad_norm), norms["zero1"])
         # ... and the update against the bf16 run of the same strategy: two roundings (8 vs 11 significant bits) of one computation
         assert diff(full, finals["zero1"]) < 0.15, diff(full, finals["zero1"])
+        fp16_zero1 = full
+        model, eng, _, full = train("zero3", dtype=torch.float16)   # ZeRO-3 in fp16: the 16-bit shard is fp16, same arithmetic as ZeRO-2
+        assert eng._w16.dtype == torch.float16 and eng.loss_scaler.skipped_steps == 0
+        assert diff(full, fp16_zero1) < 1e-2, diff(full, fp16_zero1)
         for strategy, kw in tail:
             _, eng, _, full = train(strategy, side=True, **kw)
             assert torch.equal(full, finals["zero2" if strategy == "zero3" else strategy]), ("side stream", strategy, kw)
