@@ -106,3 +106,31 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_hot_kernels_are_tcgen05_and_tma_in_the_shipped_sass():
+    """The dense contractions must run on the 5th-generation tensor cores fed by TMA: every GEMM and attention kernel of BOTH shipped
+    libraries holds tcgen05.mma (SASS UTCHMMA) and TMA loads (UTMALDG) with TMEM reads (LDTM), and no kernel anywhere falls back to
+    the legacy warp-level HMMA path (B200_PROFILING.md's mnemonics; scripts/dev/sass_histogram.py is the committed listing)."""
+    import importlib.util
+    import shutil
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    from multimodal_llm_pretraining_b200 import _lib
+    from multimodal_llm_pretraining_b200.csrc import build
+
+    build.build()
+    spec = importlib.util.spec_from_file_location("sass_histogram", ROOT / "scripts" / "dev" / "sass_histogram.py")
+    sh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sh)
+    for lib in (_lib.LIB_PATH, _lib.LIB_PATH_FP16):
+        ks = sh.histogram(lib)
+        names = sh.demangle(list(ks))
+        hot = 0
+        for (_, c), nm in zip(ks.items(), names):
+            assert c.get("HMMA", 0) == 0, f"{lib.name}: legacy mma.sync in {nm[:80]}"
+            if re.search(r"b200::(gemm_kernel|attn_fwd\w*_kernel|attn_bwd\w*_kernel)\b", nm):
+                hot += 1
+                assert c.get("UTCHMMA", 0) > 0 and c.get("UTMALDG", 0) > 0 and c.get("LDTM", 0) > 0, f"{lib.name}: {nm[:80]} {dict(c)}"
+        assert hot >= 30, (lib.name, hot)  # 25 GEMM variants + the attention forward / backward kernels
