@@ -134,3 +134,28 @@ def test_hot_kernels_are_tcgen05_and_tma_in_the_shipped_sass():
                 hot += 1
                 assert c.get("UTCHMMA", 0) > 0 and c.get("UTMALDG", 0) > 0 and c.get("LDTM", 0) > 0, f"{lib.name}: {nm[:80]} {dict(c)}"
         assert hot >= 30, (lib.name, hot)  # 25 GEMM variants + the attention forward / backward kernels
+
+
+def test_no_register_spills_outside_the_known_wide_layernorm_variants():
+    """ptxas -v (the build keeps its log next to every object): register spills stay <= 16 B for every kernel except the wide
+    ln_bwd_kernel<NV, NA> variants that no BASELINE config launches (profiles/r02_resource_usage.txt lists all of them)."""
+    from multimodal_llm_pretraining_b200.csrc import build
+
+    build.build()
+    logs = sorted(build.OBJ_DIR.glob("*.ptxas.log"))
+    if len(logs) < len(build.SOURCES):
+        pytest.skip("library was not compiled in this checkout (prebuilt .so): no ptxas logs")
+    name, seen = None, 0
+    for f in logs:
+        for ln in f.read_text().splitlines():
+            m = re.search(r"Compiling entry function '(\S+)'", ln)
+            if m:
+                name = m.group(1)
+                continue
+            m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", ln)
+            if m and name:
+                seen += 1
+                if int(m.group(2)) > 16:
+                    assert "ln_bwd_kernel" in name and not re.search(r"ln_bwd_kernelILi[12]E", name), (name, m.group(2))
+                name = None
+    assert seen >= 90
