@@ -477,10 +477,7 @@ extern "C" int b200_layernorm_bwd(const void* x, const float* mean, const float*
             case 1: LAUNCH(1, 1); break;
             case 2: LAUNCH(2, 1); break;
             case 3: LAUNCH(3, 1); break;
-            case 4: LAUNCH(4, 1); break;
-            case 5: LAUNCH(5, 1); break;
-            case 6: LAUNCH(6, 1); break;
-            case 7: case 8: LAUNCH(8, 1); break;
+            case 4: LAUNCH(4, 1); break;  // pick_group keeps nv <= 4 for every cols <= 8192
             default: return fail(-1, "layernorm_bwd: unsupported cols %d", cols);
         }
     } else {

@@ -158,4 +158,4 @@ def test_no_register_spills_outside_the_known_wide_layernorm_variants():
                 if int(m.group(2)) > 16:
                     assert "ln_bwd_kernel" in name and not re.search(r"ln_bwd_kernelILi[12]E", name), (name, m.group(2))
                 name = None
-    assert seen >= 90
+    assert seen >= 85
