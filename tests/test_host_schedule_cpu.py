@@ -635,3 +635,33 @@ def test_neox_schedule_vs_fp32_oracle_other_head_shapes(K, nh, h, pct):
         if n.endswith("query_key_value.bias"):
             a, b = a.view(nh, 3, -1)[:, [0, 2]], b.view(nh, 3, -1)[:, [0, 2]]
         assert rel(a, b) <= 2e-2, (n, rel(a, b))
+
+
+def test_engine_single_process_equals_the_hand_written_loop(K, gold):
+    """manual_training_step x ga + manual_optimization_step == the reference harness's statements written out (loss / ga backward,
+    clip_grad_norm_, optimizer.step, scheduler.step, zero_grad; src/benchmarking/utils.py:61-80), with and without clipping."""
+    from multimodal_llm_pretraining_b200.engine import TrainEngine
+    from multimodal_llm_pretraining_b200.optim import get_scheduler
+
+    b = gold["batches"]
+    for max_norm in (1.0, 0.0):
+        ma, mb = _neox(gold), _neox(gold)
+        oa = CpuAdam(ma.parameters(), lr=1e-3, betas=(0.9, 0.95))
+        ob = CpuAdam(mb.parameters(), lr=1e-3, betas=(0.9, 0.95))
+        sa = get_scheduler("cosine_with_min_lr", oa, 1, 10, {"min_lr_rate": 0.1})
+        sb = get_scheduler("cosine_with_min_lr", ob, 1, 10, {"min_lr_rate": 0.1})
+        eng = TrainEngine(ma, oa, sa, max_grad_norm=max_norm, gradient_accumulation_steps=2, strategy="none")
+        for step in range(2):
+            for ids in (b[step], b[step + 1]):
+                eng.manual_training_step({"input_ids": ids, "labels": ids})
+                (mb(input_ids=ids, labels=ids).loss / 2).backward()
+            assert eng.manual_optimization_step()
+            if max_norm > 0:
+                norm = mb.clip_grad_norm_(max_norm)
+                assert float(norm) == float(eng.last_grad_norm)
+            ob.step()
+            sb.step()
+            mb.zero_grad()
+            assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+        assert torch.equal(ma.flat.master, mb.flat.master) and torch.equal(ma.flat.shadow, mb.flat.shadow)
+        assert eng.micro == 4 and oa._step == 2
