@@ -665,3 +665,71 @@ def test_engine_single_process_equals_the_hand_written_loop(K, gold):
             assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
         assert torch.equal(ma.flat.master, mb.flat.master) and torch.equal(ma.flat.shadow, mb.flat.shadow)
         assert eng.micro == 4 and oa._step == 2
+
+
+def _dp_worker4(rank, world, port, q):
+    """Four ranks: interior slices (ranks 1, 2) exist only beyond two ranks — packed-shard offsets, gather order, owned masks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        cpu_kernels.install()
+        from multimodal_llm_pretraining_b200.engine import TrainEngine
+
+        steps, ga = 2, 2
+        data = torch.randint(2, TINY["vocab_size"], (steps, ga, world, 2, 17), generator=torch.Generator().manual_seed(11))
+        init = _build("neox").flat.master.clone()
+        keep = _noise_mask(_build("neox"))
+
+        def train(strategy, side=False, **kw):
+            model = _build("neox")
+            opt = CpuAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+            eng = TrainEngine(model, opt, None, max_grad_norm=0.5, gradient_accumulation_steps=ga, strategy=strategy, **kw)
+            if side:
+                _fake_side_stream(eng)
+            for s in range(steps):
+                for m in range(ga):
+                    eng.manual_training_step({"input_ids": data[s, m, rank], "labels": data[s, m, rank]})
+                assert eng.manual_optimization_step()
+            full = model.flat.materialize_master().clone()
+            lst = [torch.empty_like(full) for _ in range(world)]
+            dist.all_gather(lst, full)
+            assert all(torch.equal(lst[0], x) for x in lst), (strategy, "ranks hold different parameters")
+            return eng, opt, full
+
+        def diff(a, b):
+            ua, ub = (a - init)[keep], (b - init)[keep]
+            return ((ua - ub).norm() / ub.norm()).item()
+
+        _, _, ddp = train("ddp")
+        _, o1, z1 = train("zero1")
+        assert o1._m.numel() * world <= init.numel() and diff(z1, ddp) < 1e-2       # gloo emulates both with the same all-reduce: ~0
+        _, _, z1s = train("zero1", shard_master=True)
+        assert torch.equal(z1s, z1)
+        _, _, z2 = train("zero2")
+        assert diff(z2, ddp) < 1e-2
+        e3, o3, z3 = train("zero3")
+        assert torch.equal(z3, z2) and e3._w16.numel() == o3._m.numel() == o3._p32.numel()
+        _, _, z3s = train("zero3", side=True)                                      # LAST: torch.cuda stays patched
+        assert torch.equal(z3s, z2)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "".join(traceback.format_exception(e))[-2500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_real_module_through_the_engine_world4():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker4, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(4)], res
